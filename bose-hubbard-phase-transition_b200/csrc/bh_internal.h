@@ -1,0 +1,121 @@
+// bh_internal.h -- private definitions shared by the translation units of libbh_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bh_b200.h"
+
+#define BH_MAX_SITES 16   // packed state = 16 nibbles in one 64-bit word
+#define BH_MAX_BOSONS 15  // one nibble per site
+#define BH_MAX_NCV 128    // Krylov basis columns held by the Lanczos workspace
+
+// ---- ranking / lattice tables, one copy in device global memory, staged to shared memory by kernels ----
+struct BhTables {
+    int m, n;
+    // f[q][R] = [R > 0] * C(R - 1 + m - 1 - q, m - 1 - q): number of basis states that precede, on site q,
+    // a state with R bosons on the sites after q (descending-lexicographic rank = sum_q f[q][R_q]).
+    int f[BH_MAX_SITES][BH_MAX_BOSONS + 3];
+    // w[dst][src]: how many times the ordered bond appears in the neighbour list, both directions summed
+    // (the reference pushes (index,k) and (k,index) for every listed neighbour, src/hamiltonian.cpp:184-185).
+    unsigned char w[BH_MAX_SITES][BH_MAX_SITES];
+    int nbonds;  // ordered pairs with w > 0
+    // sq[a] = sqrt(a) for the amplitudes sqrt((n_dst + 1) * n_src), a <= 16 * 15
+    double sq[256];
+    double logp[BH_MAX_SITES];  // log(prime_i), host glibc values (src/hamiltonian.cpp:94,144)
+};
+
+struct bh_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+
+    // system
+    int m = 0, n = 0;
+    int64_t D = 0;
+    int64_t ld = 0;  // padded vector length (multiple of 32 doubles)
+    std::vector<int> nbr_ptr, nbr_idx;
+    BhTables h_tab;
+    BhTables* d_tab = nullptr;
+    int max_row = 0;  // max entries per row of H (incl. diagonal)
+
+    uint64_t* d_states = nullptr;  // packed occupations, LEX order
+    double* d_dU = nullptr;        // sum_i n_i (n_i + 1)
+    // H pattern = JH u diagonal, LEX order, ascending columns
+    int64_t nnzH = 0, nnzJ = 0;
+    int* d_rowptr = nullptr;
+    int* d_col = nullptr;
+    double* d_valJ = nullptr;  // J = 1 values (0 on the diagonal slot)
+    int* d_diagpos = nullptr;  // position of the diagonal entry of each row
+    double* d_valH = nullptr;  // values of the currently materialised H(cJ,cU,cmu)
+    double cur_cJ = 0, cur_cU = 0, cur_cmu = 0;
+    bool valH_valid = false;
+
+    // orderings (lazy): perm_tag[i] = LEX index of the i-th smallest tag, inv_tag = inverse
+    double* d_tags = nullptr;
+    int* d_perm_tag = nullptr;
+    int* d_inv_tag = nullptr;
+
+    // Lanczos workspace (lazy)
+    int ws_ncv = 0;
+    double* d_V = nullptr;      // (ws_ncv + 1) columns of ld doubles
+    double* d_w = nullptr;      // work vector
+    double* d_f = nullptr;      // residual vector
+    double* d_scal = nullptr;   // device scalars (see lanczos.cu)
+    double* d_part = nullptr;   // per-block partial sums
+    unsigned int* d_counter = nullptr;
+    double* d_small = nullptr;  // small matrices uploaded from the host (Y, coefficients)
+    double* d_x = nullptr;      // staging vectors for host-pointer entry points
+    double* d_y = nullptr;
+    double* h_pinned = nullptr;  // pinned host staging
+    size_t h_pinned_bytes = 0;
+};
+
+// ---- error helpers ----
+int bh_fail(bh_ctx* ctx, int code, const std::string& msg);
+#define BH_CUDA(ctx, expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return bh_fail((ctx), BH_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+#define BH_TRY(expr)                 \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != BH_OK) return _rc; \
+    } while (0)
+#define BH_LAUNCHED(ctx) ((ctx)->launches++)
+
+// ---- internal entry points (defined across the .cu files) ----
+int bh_release_system(bh_ctx* ctx);
+int bh_build_basis(bh_ctx* ctx);          // K1: states, dU
+int bh_build_hamiltonian(bh_ctx* ctx);    // K2: pattern, J values
+int bh_ensure_orderings(bh_ctx* ctx);     // tags, radix sort, permutations
+int bh_materialise_H(bh_ctx* ctx, double cJ, double cU, double cmu);
+int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x_dev, double* y_dev,
+                 double xscale_unused = 1.0);
+int bh_ensure_workspace(bh_ctx* ctx, int ncv);
+int bh_ensure_staging(bh_ctx* ctx);
+// permute between LEX (device) and `order`: dst[pos] = src[lex(pos)] (to_order) or dst[lex(pos)] = src[pos]
+int bh_permute_vec(bh_ctx* ctx, int order, bool to_order, const double* src_dev, double* dst_dev);
+// eigensolve leaving the Ritz data on the device; see lanczos.cu
+struct BhSolve {
+    std::vector<double> evals;  // nev ascending
+    std::vector<double> Y;      // ncv x nev Ritz coefficient vectors (column-major)
+    int ncv = 0, nev = 0;
+    bh_eigs_info info{};
+};
+int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
+               BhSolve* out);
+// x_dev = V * Y[:, col]  (Ritz vector in LEX order)
+int bh_ritz_vector(bh_ctx* ctx, const BhSolve& s, int col, double* x_dev);
+int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host);
+
+// host-side small dense symmetric eigen-decomposition (ascending; vectors in columns of v, column-major)
+void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::vector<double>& v);

@@ -1,0 +1,435 @@
+// lanczos.cu -- K5/K6: FP64 thick-restart Lanczos on the GPU with Spectra's parameters and stopping rule.
+//
+// Replaces Op::IRLM_eigen -> Spectra::GenEigsSolver (reference src/operator.cpp:22-33) for the symmetric H.
+// The CPU statement followed is Spectra's symmetric solver: start vector v = A v0 / |A v0| with v0 the
+// LCG(seed 0) vector (HermEigsBase.h:331-336, LinAlg/Arnoldi.h:132-180), the Lanczos step of
+// LinAlg/Lanczos.h:59-184 (three-term recurrence, then a full re-orthogonalisation correction of the
+// residual against every basis vector), Ritz pairs of the projected matrix, convergence when
+// |last-row Ritz component| * |f| < tol * max(eps^(2/3), |theta|) (HermEigsBase.h:152-169), restart size
+// nev + min(nconv, (ncv - nev)/2) (HermEigsBase.h:172-196).  The implicit restart with exact shifts
+// (HermEigsBase.h:102-148) is done in its mathematically equivalent thick-restart form: keep the first k
+// Ritz vectors V <- V Y_k (K6), the projected matrix becomes diag(theta) plus one coupling row.
+//
+// Device design: all vectors and the recurrence scalars (alpha, beta, re-orthogonalisation coefficients)
+// stay in HBM; a Lanczos step is 7 launches with no host synchronisation (each reduction kernel finishes
+// in its last-arriving block, deterministically); the host reads the ncv-sized scalar arrays once per
+// restart, solves the <=128 x 128 projected problem and uploads the Ritz coefficients.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <limits>
+
+#include "device_utils.cuh"
+
+#define NC (BH_MAX_NCV + 2)
+// layout of ctx->d_scal (doubles)
+#define S_ALPHA 0            // alpha[i]            = T(i,i)
+#define S_BETA (NC)          // beta[i+1] = |f| after step i ; beta[0] = |A v0|
+#define S_OFFD (2 * NC)      // offd[i]             = T(i,i-1) including the re-orthogonalisation correction
+#define S_VF (3 * NC)        // coefficients of the last re-orthogonalisation pass
+#define S_FLAG (4 * NC)      // [0] breakdown flag
+#define S_TOTAL (4 * NC + 8)
+
+#define VEC_THREADS 256
+#define GT_CH 8  // columns accumulated per sweep of the transposed product
+
+static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
+
+__device__ __forceinline__ bool bh_last_block(unsigned int* counter)
+{
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+    __syncthreads();
+    return is_last;
+}
+
+// |v| -> scal[dst]  (used once for |A v0|)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_norm(int64_t D, const double* __restrict__ v, double* __restrict__ scal, int dst, double* __restrict__ part,
+       unsigned int* __restrict__ counter)
+{
+    __shared__ double scratch[32];
+    double acc = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < D; r += (int64_t)gridDim.x * blockDim.x)
+        acc += v[r] * v[r];
+    acc = bh_block_sum(acc, scratch);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    if (bh_last_block(counter)) {
+        double t = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += part[b];
+        t = bh_block_sum(t, scratch);
+        if (threadIdx.x == 0) scal[dst] = sqrt(t);
+    }
+}
+
+// V_i = f / beta  (beta = scal[S_BETA + i]); a vanishing beta raises the breakdown flag
+__global__ void __launch_bounds__(VEC_THREADS)
+k_scale(int64_t D, const double* __restrict__ f, double* __restrict__ vi, double* __restrict__ scal, int i, double thresh)
+{
+    const double beta = scal[S_BETA + i];
+    double inv = 0.0;
+    if (beta > thresh)
+        inv = 1.0 / beta;
+    else if (blockIdx.x == 0 && threadIdx.x == 0)
+        scal[S_FLAG] = 1.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < D; r += (int64_t)gridDim.x * blockDim.x)
+        vi[r] = f[r] * inv;
+}
+
+// w -= offd * V_{i-1} (optional) ; alpha_i = V_i . w
+__global__ void __launch_bounds__(VEC_THREADS)
+k_local_alpha(int64_t D, double* __restrict__ w, const double* __restrict__ vprev, const double* __restrict__ vi,
+              double* __restrict__ scal, int i, int subtract, double* __restrict__ part, unsigned int* __restrict__ counter)
+{
+    __shared__ double scratch[32];
+    const double b = subtract ? scal[S_BETA + i] : 0.0;
+    double acc = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < D; r += (int64_t)gridDim.x * blockDim.x) {
+        double wr = w[r];
+        if (subtract) {
+            wr -= b * vprev[r];
+            w[r] = wr;
+        }
+        acc += vi[r] * wr;
+    }
+    acc = bh_block_sum(acc, scratch);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    if (bh_last_block(counter)) {
+        double t = 0.0;
+        for (int bb = threadIdx.x; bb < (int)gridDim.x; bb += blockDim.x) t += part[bb];
+        t = bh_block_sum(t, scratch);
+        if (threadIdx.x == 0) {
+            scal[S_ALPHA + i] = t;
+            scal[S_OFFD + i] = b;
+        }
+    }
+}
+
+// f = w - alpha_i V_i ; beta_{i} = |f|
+__global__ void __launch_bounds__(VEC_THREADS)
+k_resid_norm(int64_t D, const double* __restrict__ w, const double* __restrict__ vi, double* __restrict__ f,
+             double* __restrict__ scal, int i, double* __restrict__ part, unsigned int* __restrict__ counter)
+{
+    __shared__ double scratch[32];
+    const double a = scal[S_ALPHA + i];
+    double acc = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < D; r += (int64_t)gridDim.x * blockDim.x) {
+        const double fr = w[r] - a * vi[r];
+        f[r] = fr;
+        acc += fr * fr;
+    }
+    acc = bh_block_sum(acc, scratch);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    if (bh_last_block(counter)) {
+        double t = 0.0;
+        for (int bb = threadIdx.x; bb < (int)gridDim.x; bb += blockDim.x) t += part[bb];
+        t = bh_block_sum(t, scratch);
+        if (threadIdx.x == 0) scal[S_BETA + i + 1] = sqrt(t);
+    }
+}
+
+// vf[0..cnt) = V[:, 0..cnt)^T f ; then alpha_i += vf[i], offd_i += vf[i-1]   (Lanczos.h:150-158,166-171)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gemv_t(int64_t D, int64_t ld, const double* __restrict__ V, int cnt, const double* __restrict__ f,
+         double* __restrict__ scal, int i, int fix_offd, double* __restrict__ part, unsigned int* __restrict__ counter)
+{
+    __shared__ double red[VEC_THREADS / 32][GT_CH];
+    // contiguous row range per block so that f stays in L1/L2 across the column sweeps
+    const int64_t per = ((D + gridDim.x - 1) / gridDim.x + 3) & ~(int64_t)3;
+    const int64_t r0 = (int64_t)blockIdx.x * per;
+    const int64_t r1 = min(r0 + per, D);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < cnt; c0 += GT_CH) {
+        double acc[GT_CH];
+#pragma unroll
+        for (int j = 0; j < GT_CH; ++j) acc[j] = 0.0;
+        const int nc = min(GT_CH, cnt - c0);
+        const double* Vc = V + (int64_t)c0 * ld;
+        if (nc == GT_CH) {
+            for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+                const double fr = f[r];
+#pragma unroll
+                for (int j = 0; j < GT_CH; ++j) acc[j] += Vc[(int64_t)j * ld + r] * fr;
+            }
+        } else {
+            for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+                const double fr = f[r];
+#pragma unroll
+                for (int j = 0; j < GT_CH; ++j)
+                    if (j < nc) acc[j] += Vc[(int64_t)j * ld + r] * fr;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < GT_CH; ++j) acc[j] = bh_warp_sum(acc[j]);
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < GT_CH; ++j) red[wid][j] = acc[j];
+        }
+        __syncthreads();
+        if (threadIdx.x < nc) {
+            double t = 0.0;
+            for (int w = 0; w < VEC_THREADS / 32; ++w) t += red[w][threadIdx.x];
+            part[(int64_t)blockIdx.x * NC + c0 + threadIdx.x] = t;
+        }
+    }
+    if (bh_last_block(counter)) {
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+            double t = 0.0;
+            for (int b = 0; b < (int)gridDim.x; ++b) t += part[(int64_t)b * NC + j];
+            scal[S_VF + j] = t;
+            if (j == i) scal[S_ALPHA + i] += t;
+            if (fix_offd && j == i - 1) scal[S_OFFD + i] += t;
+        }
+    }
+}
+
+// f -= V[:, 0..cnt) vf ; beta_i = |f|
+__global__ void __launch_bounds__(VEC_THREADS)
+k_gemv_n_norm(int64_t D, int64_t ld, const double* __restrict__ V, int cnt, double* __restrict__ f,
+              double* __restrict__ scal, int i, double* __restrict__ part, unsigned int* __restrict__ counter)
+{
+    __shared__ double coef[NC];
+    __shared__ double scratch[32];
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) coef[j] = scal[S_VF + j];
+    __syncthreads();
+    double acc = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < D; r += (int64_t)gridDim.x * blockDim.x) {
+        double fr = f[r];
+        int j = 0;
+        for (; j + 4 <= cnt; j += 4) {
+            const double v0 = V[(int64_t)j * ld + r], v1 = V[(int64_t)(j + 1) * ld + r];
+            const double v2 = V[(int64_t)(j + 2) * ld + r], v3 = V[(int64_t)(j + 3) * ld + r];
+            fr -= v0 * coef[j];
+            fr -= v1 * coef[j + 1];
+            fr -= v2 * coef[j + 2];
+            fr -= v3 * coef[j + 3];
+        }
+        for (; j < cnt; ++j) fr -= V[(int64_t)j * ld + r] * coef[j];
+        f[r] = fr;
+        acc += fr * fr;
+    }
+    acc = bh_block_sum(acc, scratch);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    if (bh_last_block(counter)) {
+        double t = 0.0;
+        for (int bb = threadIdx.x; bb < (int)gridDim.x; bb += blockDim.x) t += part[bb];
+        t = bh_block_sum(t, scratch);
+        if (threadIdx.x == 0) scal[S_BETA + i + 1] = sqrt(t);
+    }
+}
+
+// out = V[:, 0..cnt) y   (Ritz vector, HermEigsBase.h:456-479)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_lincomb(int64_t D, int64_t ld, const double* __restrict__ V, int cnt, const double* __restrict__ y,
+          double* __restrict__ out)
+{
+    __shared__ double coef[NC];
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) coef[j] = y[j];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < D; r += (int64_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int j = 0; j < cnt; ++j) acc += V[(int64_t)j * ld + r] * coef[j];
+        out[r] = acc;
+    }
+}
+
+// K6: V[:, 0..k) <- V[:, 0..ncv) Y[:, 0..k), in place (a CTA owns CR rows: it reads all their ncv entries
+// into shared memory before it writes any of them).  Y is ncv x k column-major in global memory.
+#define CR 64
+#define CK 16
+__global__ void __launch_bounds__(256)
+k_compress(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, const double* __restrict__ Y)
+{
+    extern __shared__ double sm[];
+    double* vt = sm;                      // [ncv][CR]
+    double* yc = sm + (size_t)ncv * CR;   // [CK][ncv]
+    const int64_t r0 = (int64_t)blockIdx.x * CR;
+    const int rr = threadIdx.x % CR, cg = threadIdx.x / CR;  // 4 column groups
+    for (int idx = threadIdx.x; idx < ncv * CR; idx += blockDim.x) {
+        const int j = idx / CR, r = idx % CR;
+        vt[idx] = (r0 + r < D) ? V[(int64_t)j * ld + r0 + r] : 0.0;
+    }
+    for (int c0 = 0; c0 < k; c0 += CK) {
+        const int nck = min(CK, k - c0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nck * ncv; idx += blockDim.x) yc[idx] = Y[(size_t)c0 * ncv + idx];
+        __syncthreads();
+        for (int l = cg; l < nck; l += 4) {
+            const double* yl = yc + (size_t)l * ncv;
+            double acc = 0.0;
+            for (int j = 0; j < ncv; ++j) acc += vt[j * CR + rr] * yl[j];
+            if (r0 + rr < D) V[(int64_t)(c0 + l) * ld + r0 + rr] = acc;
+        }
+    }
+}
+
+int bh_ensure_workspace(bh_ctx* ctx, int ncv)
+{
+    if (!ctx->D) return bh_fail(ctx, BH_ERR_STATE, "no system: call bh_setup first");
+    if (!ctx->d_w) BH_CUDA(ctx, cudaMalloc(&ctx->d_w, sizeof(double) * ctx->ld));
+    if (!ctx->d_f) BH_CUDA(ctx, cudaMalloc(&ctx->d_f, sizeof(double) * ctx->ld));
+    if (!ctx->d_scal) {
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_scal, sizeof(double) * S_TOTAL));
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * (size_t)NC * (ctx->sm_count * 8)));
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_counter, sizeof(unsigned int) * 4));
+        BH_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int) * 4, ctx->stream));
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_small, sizeof(double) * (size_t)NC * NC));
+    }
+    if (ncv > ctx->ws_ncv) {
+        if (ctx->d_V) cudaFree(ctx->d_V);
+        ctx->d_V = nullptr;
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_V, sizeof(double) * (size_t)ctx->ld * (ncv + 1)));
+        ctx->ws_ncv = ncv;
+    }
+    return BH_OK;
+}
+
+int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
+               BhSolve* out)
+{
+    const int64_t D = ctx->D, ld = ctx->ld;
+    // Spectra::GenEigsBase constructor checks (GenEigsBase.h:335-339), which the reference relies on
+    if (nev < 1 || nev > D - 2) return bh_fail(ctx, BH_ERR_ARG, "nev must satisfy 1 <= nev <= n - 2, n is the size of matrix");
+    if (ncv < nev + 2 || ncv > D) return bh_fail(ctx, BH_ERR_ARG, "ncv must satisfy nev + 2 <= ncv <= n, n is the size of matrix");
+    if (ncv > BH_MAX_NCV) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "ncv exceeds BH_MAX_NCV");
+    const auto t_start = std::chrono::steady_clock::now();
+    BH_TRY(bh_ensure_workspace(ctx, ncv));
+    cudaStream_t st = ctx->stream;
+    double* V = ctx->d_V;
+    double* scal = ctx->d_scal;
+    double* part = ctx->d_part;
+    unsigned int* counter = ctx->d_counter;
+    const int G = (int)std::min<int64_t>(nblocks(D, VEC_THREADS), (int64_t)ctx->sm_count * 4);
+    const double eps = std::numeric_limits<double>::epsilon();
+    const double near0 = std::numeric_limits<double>::min() * 10.0;
+    const double eps23 = std::pow(eps, 2.0 / 3.0);
+
+    BH_CUDA(ctx, cudaMemsetAsync(scal, 0, sizeof(double) * S_TOTAL, st));
+    // v0 = LCG ; f = A v0 ; beta[0] = |f|   (Arnoldi.h:147-154)
+    BH_TRY(bh_lcg_fill_dev(ctx, ctx->d_w, D));
+    BH_TRY(bh_launch_hv(ctx, cJ, cU, cmu, kernel, ctx->d_w, ctx->d_f));
+    k_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, scal, S_BETA + 0, part, counter);
+    BH_LAUNCHED(ctx);
+    int nmatvec = 1;
+
+    std::vector<double> h_scal(S_TOTAL);
+    std::vector<double> theta, coup;  // kept Ritz values and their coupling to the next vector
+    std::vector<double> T, evals, Y;
+    int from = 0, nconv = 0, iter = 0;
+    double beta_last = 0.0;
+    const size_t compress_smem = sizeof(double) * ((size_t)ncv * CR + (size_t)CK * ncv);
+    if (compress_smem > 48 * 1024)
+        BH_CUDA(ctx, cudaFuncSetAttribute(k_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compress_smem));
+
+    for (;;) {
+        for (int i = from; i < ncv; ++i) {
+            double* vi = V + (int64_t)i * ld;
+            const bool first_after_restart = (from > 0 && i == from);
+            k_scale<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, vi, scal, i, near0);
+            BH_TRY(bh_launch_hv(ctx, cJ, cU, cmu, kernel, vi, ctx->d_w));
+            ++nmatvec;
+            const int subtract = (i > 0 && !first_after_restart) ? 1 : 0;
+            k_local_alpha<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_w, i > 0 ? vi - ld : vi, vi, scal, i, subtract, part, counter);
+            k_resid_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_w, vi, ctx->d_f, scal, i, part, counter);
+            const int passes = first_after_restart ? 2 : 1;
+            for (int p = 0; p < passes; ++p) {
+                k_gemv_t<<<G, VEC_THREADS, 0, st>>>(D, ld, V, i + 1, ctx->d_f, scal, i, subtract, part, counter);
+                k_gemv_n_norm<<<G, VEC_THREADS, 0, st>>>(D, ld, V, i + 1, ctx->d_f, scal, i, part, counter);
+            }
+            ctx->launches += 3 + 2 * passes;
+        }
+        BH_CUDA(ctx, cudaGetLastError());
+        BH_CUDA(ctx, cudaMemcpyAsync(h_scal.data(), scal, sizeof(double) * S_TOTAL, cudaMemcpyDeviceToHost, st));
+        BH_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h_scal[S_FLAG] != 0.0)
+            return bh_fail(ctx, BH_ERR_NOCONV, "Lanczos breakdown (invariant subspace reached before ncv steps)");
+        // projected matrix: diag(theta) + coupling row at `from`, tridiagonal afterwards
+        T.assign((size_t)ncv * ncv, 0.0);
+        for (int l = 0; l < from; ++l) {
+            T[l + (size_t)l * ncv] = theta[l];
+            T[from + (size_t)l * ncv] = T[l + (size_t)from * ncv] = coup[l];
+        }
+        for (int i = from; i < ncv; ++i) {
+            T[i + (size_t)i * ncv] = h_scal[S_ALPHA + i];
+            if (i > from) T[i + (size_t)(i - 1) * ncv] = T[(i - 1) + (size_t)i * ncv] = h_scal[S_OFFD + i];
+        }
+        bh_sym_eig(ncv, T, evals, Y);  // ascending = Spectra's SmallestAlge selection
+        beta_last = h_scal[S_BETA + ncv];
+        nconv = 0;
+        for (int l = 0; l < nev; ++l) {
+            const double thresh = tol * std::max(eps23, std::fabs(evals[l]));
+            const double resid = std::fabs(Y[(ncv - 1) + (size_t)l * ncv]) * beta_last;
+            nconv += (resid < thresh);
+        }
+        if (nconv >= nev || iter >= maxit) break;
+        ++iter;
+        // HermEigsBase.h:172-196
+        int knew = nev;
+        for (int l = nev; l < ncv; ++l)
+            if (std::fabs(Y[(ncv - 1) + (size_t)l * ncv]) < near0) ++knew;
+        knew += std::min(nconv, (ncv - knew) / 2);
+        if (knew == 1 && ncv >= 6)
+            knew = ncv / 2;
+        else if (knew == 1 && ncv > 2)
+            knew = 2;
+        if (knew > ncv - 1) knew = ncv - 1;
+        // K6: V[:, 0..knew) <- V Y[:, 0..knew)
+        BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, Y.data(), sizeof(double) * (size_t)ncv * knew, cudaMemcpyHostToDevice, st));
+        k_compress<<<nblocks(D, CR), 256, compress_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
+        BH_LAUNCHED(ctx);
+        theta.assign(evals.begin(), evals.begin() + knew);
+        coup.resize(knew);
+        for (int l = 0; l < knew; ++l) coup[l] = beta_last * Y[(ncv - 1) + (size_t)l * ncv];
+        // the residual f and its norm carry over: V_knew = f / beta_last
+        BH_CUDA(ctx, cudaMemcpyAsync(scal + S_BETA + knew, scal + S_BETA + ncv, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        from = knew;
+    }
+    out->nev = nev;
+    out->ncv = ncv;
+    out->evals.assign(evals.begin(), evals.begin() + nev);
+    out->Y.assign(Y.begin(), Y.begin() + (size_t)ncv * nev);
+    out->info.nconv = std::min(nconv, nev);
+    out->info.nmatvec = nmatvec;
+    out->info.nrestart = iter + 1;
+    out->info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    if (nconv < nev) return bh_fail(ctx, BH_ERR_NOCONV, "Eigenvalue computation failed.");
+    return BH_OK;
+}
+
+int bh_ritz_vector(bh_ctx* ctx, const BhSolve& s, int col, double* x_dev)
+{
+    BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, s.Y.data() + (size_t)col * s.ncv, sizeof(double) * s.ncv,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    const int G = (int)std::min<int64_t>(nblocks(ctx->D, VEC_THREADS), (int64_t)ctx->sm_count * 4);
+    k_lincomb<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->D, ctx->ld, ctx->d_V, s.ncv, ctx->d_small, x_dev);
+    BH_LAUNCHED(ctx);
+    BH_CUDA(ctx, cudaGetLastError());
+    return BH_OK;
+}
+
+extern "C" int bh_eigs(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
+                       int order, double* evals, double* evecs, bh_eigs_info* info)
+{
+    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_eigs: call bh_setup first");
+    if (!evals || order < 0 || order > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_eigs: bad argument");
+    BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    BhSolve s;
+    const int rc = bh_lanczos(ctx, cJ, cU, cmu, nev, ncv, tol, maxit, kernel, &s);
+    if (info) *info = s.info;
+    if (rc != BH_OK && rc != BH_ERR_NOCONV) return rc;
+    for (size_t i = 0; i < s.evals.size(); ++i) evals[i] = s.evals[i];
+    if (evecs && !s.evals.empty()) {
+        BH_TRY(bh_ensure_staging(ctx));
+        for (int c = 0; c < nev; ++c) {
+            BH_TRY(bh_ritz_vector(ctx, s, c, ctx->d_x));
+            BH_TRY(bh_permute_vec(ctx, order, true, ctx->d_x, ctx->d_y));
+            BH_CUDA(ctx, cudaMemcpyAsync(evecs + (size_t)c * ctx->D, ctx->d_y, sizeof(double) * ctx->D,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+            BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return rc;
+}

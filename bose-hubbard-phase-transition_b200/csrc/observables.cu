@@ -1,0 +1,207 @@
+// observables.cu -- K7: ground-state observables as device reductions, and the per-point driver.
+//
+// Replaces Analysis::SPDM / braket / coherence / gap_ratios and the body of the sweep loop
+// (reference src/analysis.cpp:311-337,433-454,497-594).  The reference makes m(m+1)/2 passes over the D
+// basis states with a tag + binary search per term; here one pass per source site j accumulates every
+// <a_i^+ a_j>, i <= j, with the O(1) incremental rank.  Kept quirks: the amplitude is
+// sqrt((n_i + 1)(n_j - 1)) for i != j, terms with |phi| <= eps are skipped, and rho is
+// divided by the number of eigenvector columns (src/analysis.cpp:527).
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "device_utils.cuh"
+
+static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
+
+#define SPDM_THREADS 256
+
+template <int M>
+__global__ void __launch_bounds__(SPDM_THREADS)
+k_spdm(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restrict__ states, const double* __restrict__ phi,
+       double* __restrict__ part /* [gridDim.x][M][M] */)
+{
+    __shared__ BhTables t;
+    __shared__ double scratch[32];
+    bh_stage_tables(&t, gtab);
+    const int j = blockIdx.y;  // source site
+    const double eps = 2.220446049250313e-16;
+    double acc[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) acc[i] = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < D; k += (int64_t)gridDim.x * blockDim.x) {
+        const double pk = phi[k];
+        if (!(fabs(pk) > eps)) continue;
+        const uint64_t s = states[k];
+        const int nj = bh_occ(s, j);
+        if (nj < 1) continue;
+        int dn[M], up[M];
+        bh_rank_prefix<M>(t, s, dn, up);
+        int dnj = 0;
+#pragma unroll
+        for (int q = 0; q < M; ++q)
+            if (q == j) dnj = dn[q];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            if (i > j) continue;
+            if (i == j) {
+                acc[i] += pk * pk * t.sq[nj * nj];  // sqrt(n_j * n_j) = n_j
+            } else {
+                const int tgt = (int)k + dnj - dn[i];
+                const double pt = __ldg(phi + tgt);
+                if (fabs(pt) > eps) acc[i] += pk * pt * t.sq[(bh_occ(s, i) + 1) * (nj - 1)];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        const double v = bh_block_sum(acc[i], scratch);
+        if (threadIdx.x == 0) part[((int64_t)blockIdx.x * M + j) * M + i] = v;
+    }
+}
+
+__global__ void k_spdm_reduce(int m, int nb, const double* __restrict__ part, double inv_cols, double* __restrict__ rho)
+{
+    const int i = threadIdx.x % m, j = threadIdx.x / m;
+    if (j >= m || i > j) return;
+    double t = 0.0;
+    for (int b = 0; b < nb; ++b) t += part[((int64_t)b * m + j) * m + i];
+    t *= inv_cols;
+    rho[i + j * m] = t;  // column-major, upper triangle computed, lower mirrored (src/analysis.cpp:509-511)
+    rho[j + i * m] = t;
+}
+
+typedef void (*spdm_fn)(const BhTables*, int64_t, const uint64_t*, const double*, double*);
+static spdm_fn spdm_kernel(int m)
+{
+    switch (m) {
+        case 1: return k_spdm<1>;
+        case 2: return k_spdm<2>;
+        case 3: return k_spdm<3>;
+        case 4: return k_spdm<4>;
+        case 5: return k_spdm<5>;
+        case 6: return k_spdm<6>;
+        case 7: return k_spdm<7>;
+        case 8: return k_spdm<8>;
+        case 9: return k_spdm<9>;
+        case 10: return k_spdm<10>;
+        case 11: return k_spdm<11>;
+        case 12: return k_spdm<12>;
+        case 13: return k_spdm<13>;
+        case 14: return k_spdm<14>;
+        case 15: return k_spdm<15>;
+        case 16: return k_spdm<16>;
+    }
+    return nullptr;
+}
+
+int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
+{
+    const int m = ctx->m;
+    BH_TRY(bh_ensure_workspace(ctx, 0));
+    const int gx = (int)std::min<int64_t>(nblocks(ctx->D, SPDM_THREADS), (int64_t)ctx->sm_count * 2);
+    double* d_part = nullptr;
+    double* d_rho = nullptr;
+    BH_CUDA(ctx, cudaMalloc(&d_part, sizeof(double) * (size_t)gx * m * m));
+    BH_CUDA(ctx, cudaMalloc(&d_rho, sizeof(double) * m * m));
+    dim3 grid(gx, m);
+    spdm_kernel(m)<<<grid, SPDM_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->D, ctx->d_states, phi_dev, d_part);
+    k_spdm_reduce<<<1, m * m, 0, ctx->stream>>>(m, gx, d_part, 1.0 / (double)ncols, d_rho);
+    ctx->launches += 2;
+    BH_CUDA(ctx, cudaGetLastError());
+    BH_CUDA(ctx, cudaMemcpyAsync(rho_host, d_rho, sizeof(double) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_part);
+    cudaFree(d_rho);
+    return BH_OK;
+}
+
+extern "C" int bh_spdm(bh_ctx* ctx, int order, const double* phi, int ncols, double* rho)
+{
+    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_spdm: call bh_setup first");
+    if (!phi || !rho || ncols < 1 || order < 0 || order > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_spdm: bad argument");
+    BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    BH_TRY(bh_ensure_staging(ctx));
+    BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_y, phi, sizeof(double) * ctx->D, cudaMemcpyHostToDevice, ctx->stream));
+    BH_TRY(bh_permute_vec(ctx, order, false, ctx->d_y, ctx->d_x));
+    return bh_spdm_dev(ctx, ctx->d_x, ncols, rho);
+}
+
+// ---- host scalars ----
+extern "C" int bh_gap_ratios(const double* evals, int nb_eigen, double* ratios)
+{
+    if (!evals || !ratios || nb_eigen < 3) return BH_ERR_ARG;
+    std::vector<double> s(evals, evals + nb_eigen);
+    std::sort(s.begin(), s.end());
+    for (int i = 1; i < nb_eigen - 1; ++i) {
+        const double up = s[i + 1] - s[i], dn = s[i] - s[i - 1];
+        const double lo = std::min(up, dn), hi = std::max(up, dn);
+        ratios[i - 1] = (hi != 0) ? lo / hi : 0.0;
+    }
+    return BH_OK;
+}
+
+extern "C" int bh_condensate_fraction(int m, const double* rho, double* out)
+{
+    if (!rho || !out || m < 1) return BH_ERR_ARG;
+    std::vector<double> a(rho, rho + (size_t)m * m), ev, vec;
+    double tr = 0;
+    for (int i = 0; i < m; ++i) tr += rho[i + (size_t)i * m];
+    bh_sym_eig(m, a, ev, vec);
+    double best = ev[0];
+    for (int i = 1; i < m; ++i)
+        if (std::fabs(best) < std::fabs(ev[i])) best = ev[i];
+    *out = std::fabs(best / tr);
+    return BH_OK;
+}
+
+extern "C" int bh_coherence(int m, const double* rho, double* out)
+{
+    if (!rho || !out || m < 1) return BH_ERR_ARG;
+    double all = 0, diag = 0;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) {
+            const double p = rho[i + (size_t)j * m] * rho[j + (size_t)i * m];
+            all += p;
+            if (i == j) diag += p;
+        }
+    *out = (all - diag) / all;
+    return BH_OK;
+}
+
+// ---- one grid point / a shard of grid points ----
+extern "C" int bh_point(bh_ctx* ctx, double cJ, double cU, double cmu, int nb_eigen, int kernel, double* out3,
+                        double* evals, double* rho, bh_eigs_info* info)
+{
+    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_point: call bh_setup first");
+    if (!out3 || nb_eigen < 3) return bh_fail(ctx, BH_ERR_ARG, "bh_point: bad argument");
+    BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    BhSolve s;
+    // Op::IRLM_eigen: nev = nb_eigen, ncv = 2 nb_eigen + 1, Spectra defaults tol 1e-10, maxit 1000
+    const int rc = bh_lanczos(ctx, cJ, cU, cmu, nb_eigen, 2 * nb_eigen + 1, 1e-10, 1000, kernel, &s);
+    if (info) *info = s.info;
+    if (rc != BH_OK) return rc;
+    std::vector<double> ratios(nb_eigen - 2);
+    bh_gap_ratios(s.evals.data(), nb_eigen, ratios.data());
+    double g = 0;
+    for (double r : ratios) g += r;
+    out3[0] = ratios.empty() ? 0.0 : g / (double)ratios.size();
+    BH_TRY(bh_ensure_staging(ctx));
+    BH_TRY(bh_ritz_vector(ctx, s, 0, ctx->d_x));
+    std::vector<double> r((size_t)ctx->m * ctx->m);
+    BH_TRY(bh_spdm_dev(ctx, ctx->d_x, nb_eigen, r.data()));
+    bh_condensate_fraction(ctx->m, r.data(), &out3[1]);
+    bh_coherence(ctx->m, r.data(), &out3[2]);
+    if (evals) std::copy(s.evals.begin(), s.evals.end(), evals);
+    if (rho) std::copy(r.begin(), r.end(), rho);
+    return BH_OK;
+}
+
+extern "C" int bh_points(bh_ctx* ctx, const double* cJ, const double* cU, const double* cmu, int64_t npoints, int nb_eigen,
+                         int kernel, double* out3, bh_eigs_info* infos)
+{
+    if (!ctx || !cJ || !cU || !cmu || !out3 || npoints < 0) return bh_fail(ctx, BH_ERR_ARG, "bh_points: bad argument");
+    for (int64_t p = 0; p < npoints; ++p)
+        BH_TRY(bh_point(ctx, cJ[p], cU[p], cmu[p], nb_eigen, kernel, out3 + 3 * p, nullptr, nullptr, infos ? infos + p : nullptr));
+    return BH_OK;
+}

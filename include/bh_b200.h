@@ -1,0 +1,131 @@
+/* bh_b200.h -- C ABI of libbh_b200.so, the B200-native exact-diagonalisation hot path of
+ * Bose-Hubbard-Phase-Transition (Fock basis -> Hamiltonian -> lowest eigenpairs -> ground-state
+ * observables, swept over a (J, U, mu) grid).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no exceptions.
+ * The reference has no FFI layer; each entry point below names the reference interface it
+ * replaces (paths relative to the reference repository root).  The C++ shim under
+ * bose-hubbard-phase-transition_b200/host/ keeps the reference's own signatures (namespaces BH, Op,
+ * Analysis, class Neighbours, the CLI) on top of this ABI; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every function returns BH_OK (0) or a negative BH_ERR_* code; bh_last_error() gives the text;
+ *  - all pointers are HOST pointers unless the name ends in _dev (device pointers, used by the
+ *    benchmark and by callers that keep vectors resident in HBM);
+ *  - there is NO CPU fallback: without a usable CUDA device bh_ctx_create fails;
+ *  - a context owns one GPU and one "system" (m sites, n bosons, neighbour list) at a time; calls on
+ *    one context are serialised by the caller (the reference's OpenMP threads map to one context
+ *    per thread/GPU);
+ *  - `order` selects the basis ordering used for every per-state array crossing the boundary:
+ *      BH_ORDER_LEX          descending-lexicographic enumeration order (src/hamiltonian.cpp:60-85),
+ *                            the order used internally on the device;
+ *      BH_ORDER_TAG_SORTED   ascending prime-log tag (what BH::sort_basis intends, src/hamiltonian.cpp:109-123);
+ *      BH_ORDER_REF_SCATTER  the order the unmodified BH::fixed_set_basis really returns (its in-place
+ *                            permutation applies the inverse).
+ *  - matrices are returned in compressed-column form with ascending inner indices, exactly the arrays of
+ *    an Eigen::SparseMatrix<double> (outerIndexPtr / innerIndexPtr / valuePtr); H is symmetric so this is
+ *    also its CSR form.
+ */
+#ifndef BH_B200_H
+#define BH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bh_ctx bh_ctx;
+
+enum { BH_OK = 0, BH_ERR_ARG = -1, BH_ERR_CUDA = -2, BH_ERR_STATE = -3, BH_ERR_NOCONV = -4, BH_ERR_UNSUPPORTED = -5 };
+enum { BH_ORDER_LEX = 0, BH_ORDER_TAG_SORTED = 1, BH_ORDER_REF_SCATTER = 2 };
+enum { BH_TERM_J = 0, BH_TERM_U = 1, BH_TERM_MU = 2 };
+/* H.v kernels: stored CSR (K3) or matrix-free on-the-fly (K4) */
+enum { BH_HV_STORED = 0, BH_HV_MATRIX_FREE = 1 };
+
+/* ---- context ------------------------------------------------------------------------------- */
+int bh_ctx_create(int device, bh_ctx** ctx);
+int bh_ctx_destroy(bh_ctx* ctx);
+/* text of the last error on this context (ctx may be NULL: error of the last failed bh_ctx_create) */
+const char* bh_last_error(const bh_ctx* ctx);
+/* use an existing CUDA stream (cudaStream_t) for every launch of this context; NULL = own stream */
+int bh_ctx_set_stream(bh_ctx* ctx, void* cuda_stream);
+/* number of kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t bh_ctx_launch_count(const bh_ctx* ctx);
+
+/* ---- geometry: replaces class Neighbours (include/neighbours.hpp:12-63, src/neighbours.cpp) ----- */
+/* Fill a CSR-style neighbour list: nbr_ptr[m+1], nbr_idx[nbr_ptr[m]].  Call with nbr_idx == NULL to get
+ * the sizes only.  Entry order per site follows the reference (left, right[, up, down[, front, back]]). */
+int bh_neighbours_chain(int m, int closed, int* nbr_ptr, int* nbr_idx);                    /* src/neighbours.cpp:21-34 */
+int bh_neighbours_rect(int lx, int ly, int lz, int closed, int* nbr_ptr, int* nbr_idx);    /* :40-120, any lx*ly*lz */
+
+/* ---- Fock basis: replaces BH::dimension / BH::fixed_set_basis / BH::search_tag -------------- */
+int bh_dimension(int m, int n, int64_t* D);                                                /* src/hamiltonian.cpp:39-54 */
+/* Build the system on the device: basis, ranking tables, diagonals, hopping matrix (K1, K2). */
+int bh_setup(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int* nbr_idx);
+/* tags[D], basis[m*D] column-major (state k = column k), src/hamiltonian.cpp:143-149.  Either may be NULL. */
+int bh_basis(bh_ctx* ctx, int order, double* tags, double* basis);
+/* ranks[count] = index (in `order`) of each of `count` occupation vectors given as columns of
+ * states[m*count] (doubles, like the reference's basis); -1 if it is not a basis state.
+ * Replaces calculate_tag + search_tag (src/hamiltonian.cpp:91-97,126-140). */
+int bh_rank(bh_ctx* ctx, int order, const double* states, int64_t count, int32_t* ranks);
+
+/* ---- Hamiltonian: replaces BH::fixed_bosons_hamiltonian (src/hamiltonian.cpp:170-256) -------- */
+int bh_term_nnz(bh_ctx* ctx, int term, int64_t* nnz);
+/* One term scaled by coef, exactly the matrix the reference builds for (J,0,0), (0,U,0) or (0,0,mu). */
+int bh_term_csc(bh_ctx* ctx, int term, double coef, int order, int32_t* outer, int32_t* inner, double* val);
+/* H = JH*cJ + UH*cU + uH*cmu with the union pattern and explicit zeros of src/analysis.cpp:311;
+ * nnz(H) = nnz(JH) + D. */
+int bh_hamiltonian_nnz(bh_ctx* ctx, int64_t* nnz);
+int bh_hamiltonian_csc(bh_ctx* ctx, double cJ, double cU, double cmu, int order, int32_t* outer, int32_t* inner,
+                       double* val);
+
+/* ---- H.v: replaces Spectra::SparseGenMatProd::perform_op (MatOp/SparseGenMatProd.h:81-86) ---- */
+/* y = (JH*cJ + UH*cU + uH*cmu) x with host vectors in `order` (copies included: this is the MatOp seam). */
+int bh_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, int order, const double* x, double* y);
+/* Same with device vectors in LEX order, launched on the context's stream, no synchronisation. */
+int bh_hv_dev(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x_dev, double* y_dev);
+
+/* ---- eigensolver: replaces Op::IRLM_eigen (src/operator.cpp:22-33) --------------------------- */
+typedef struct bh_eigs_info {
+    int32_t nconv;     /* converged wanted pairs */
+    int32_t nmatvec;   /* H.v applications */
+    int32_t nrestart;  /* restarts (Spectra's num_iterations) */
+    int32_t reserved;
+    double seconds;    /* device+host wall time of the solve */
+} bh_eigs_info;
+/* nev smallest eigenvalues (ascending) of H(cJ,cU,cmu); thick-restart Lanczos with Spectra's
+ * parameters (ncv, tol, maxit; HermEigsBase.h:360-385).  evecs may be NULL, else D*nev column-major in
+ * `order`.  kernel selects the H.v implementation.  Returns BH_ERR_NOCONV if fewer than nev converged
+ * (the reference throws std::runtime_error("Eigenvalue computation failed.")), BH_ERR_ARG when
+ * nev/ncv violate Spectra's constructor checks (nev + 2 <= ncv <= D for the general solver). */
+int bh_eigs(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
+            int order, double* evals, double* evecs, bh_eigs_info* info);
+
+/* ---- observables: replaces Analysis::SPDM/braket/coherence/gap_ratios (src/analysis.cpp:433-594) */
+/* rho[m*m] column-major from a state vector phi (host, `order`), divided by ncols (the reference divides
+ * by eigenvectors.cols() = nb_eigen, src/analysis.cpp:527). */
+int bh_spdm(bh_ctx* ctx, int order, const double* phi, int ncols, double* rho);
+int bh_gap_ratios(const double* evals, int nb_eigen, double* ratios /* nb_eigen-2 */);   /* :433-454 */
+int bh_condensate_fraction(int m, const double* rho, double* out);                       /* :331-334 */
+int bh_coherence(int m, const double* rho, double* out);                                 /* :542-556 */
+
+/* ---- sweep: replaces the body and loop of Analysis::calculate_and_save (src/analysis.cpp:266-387) */
+/* One grid point: eigensolve + gap ratio + SPDM + condensate fraction + coherence.
+ * out3 = {gap_ratio, condensate_fraction, coherence}; evals[nb_eigen] and rho[m*m] optional. */
+int bh_point(bh_ctx* ctx, double cJ, double cU, double cmu, int nb_eigen, int kernel, double* out3, double* evals,
+             double* rho, bh_eigs_info* info);
+/* A list of grid points on this context (the shard of one GPU): cJ/cU/cmu[npoints] -> out3[3*npoints]. */
+int bh_points(bh_ctx* ctx, const double* cJ, const double* cU, const double* cmu, int64_t npoints, int nb_eigen,
+              int kernel, double* out3, bh_eigs_info* infos /* may be NULL */);
+
+/* ---- benchmark helpers (device-resident, used by bench.py) --------------------------------------- */
+/* Fill x_dev[D] with Spectra's LCG(seed 0) uniform(-0.5,0.5) sequence (Util/SimpleRandom.h:30-64), LEX order. */
+int bh_lcg_fill_dev(bh_ctx* ctx, double* x_dev, int64_t count);
+/* Algorithmic bytes of one H.v: stored = 12*nnz(H) + 4*(D+1) + 16*D, matrix-free = 16*D. */
+int bh_hv_algorithmic_bytes(bh_ctx* ctx, int kernel, int64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BH_B200_H */
