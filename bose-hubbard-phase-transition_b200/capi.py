@@ -19,7 +19,7 @@ HV_STORED, HV_MATRIX_FREE = 0, 1
 
 # every symbol include/bh_b200.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [
-    "bh_ctx_create", "bh_ctx_destroy", "bh_last_error", "bh_ctx_set_stream", "bh_ctx_launch_count",
+    "bh_ctx_create", "bh_ctx_destroy", "bh_last_error", "bh_ctx_set_stream", "bh_ctx_launch_count", "bh_ctx_transfer_bytes",
     "bh_neighbours_chain", "bh_neighbours_rect", "bh_dimension", "bh_setup", "bh_basis", "bh_rank",
     "bh_term_nnz", "bh_term_csc", "bh_hamiltonian_nnz", "bh_hamiltonian_csc", "bh_hv", "bh_hv_dev", "bh_eigs",
     "bh_spdm", "bh_gap_ratios", "bh_condensate_fraction", "bh_coherence", "bh_point", "bh_points",
@@ -60,6 +60,7 @@ def load():
     L.bh_ctx_set_stream.argtypes = [vp, vp]
     L.bh_ctx_launch_count.argtypes = [vp]
     L.bh_ctx_launch_count.restype = C.c_int64
+    L.bh_ctx_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.bh_neighbours_chain.argtypes = [C.c_int, C.c_int, vp, vp]
     L.bh_neighbours_rect.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.bh_dimension.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64)]
@@ -172,6 +173,11 @@ class Context:
 
     def launch_count(self):
         return self.L.bh_ctx_launch_count(self.h)
+
+    def transfer_bytes(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.L.bh_ctx_transfer_bytes(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def setup(self, m, n, nbr=None):
         ptr, idx = nbr if nbr is not None else neighbours_chain(m)

@@ -11,7 +11,7 @@
 
 #define BH_MAX_SITES 16   // packed state = 16 nibbles in one 64-bit word
 #define BH_MAX_BOSONS 15  // one nibble per site
-#define BH_MAX_NCV 128    // Krylov basis columns held by the Lanczos workspace
+#define BH_MAX_NCV 512    // Krylov basis columns held by the Lanczos workspace
 
 // ---- ranking / lattice tables, one copy in device global memory, staged to shared memory by kernels ----
 struct BhTables {
@@ -35,6 +35,7 @@ struct bh_ctx {
     bool own_stream = false;
     std::string err;
     int64_t launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied across PCIe by this context
 
     // system
     int m = 0, n = 0;
@@ -44,6 +45,20 @@ struct bh_ctx {
     BhTables h_tab;
     BhTables* d_tab = nullptr;
     int max_row = 0;  // max entries per row of H (incl. diagonal)
+    int hv_variant = 2;  // stored H.v: 0 = CSR-stream, 1 = TMA-staged CSR-stream, 2 = SELL-32 (default; env BH_HV_VARIANT)
+    int hv_stages = 3;   // ring depth of the TMA variant (env BH_HV_STAGES)
+    int tile_cap = 0;    // entries per shared-memory stage of the TMA variant
+    size_t hv_smem_configured = 0;
+    // SELL-32 copy of the stored H (variant 2): slices of 32 consecutive rows, column-major inside a slice,
+    // padded to the longest row of the slice (padding = zero value pointing at the row's own column)
+    int64_t sell_nslices = 0, sell_entries = 0;
+    int* d_sell_ptr = nullptr;      // [nslices + 1] entry offset of each slice
+    int* d_sell_col = nullptr;
+    double* d_sell_valJ = nullptr;
+    double* d_sell_valH = nullptr;
+    int* d_sell_diag = nullptr;     // [D] position of each row's diagonal entry
+    bool sell_valid = false;
+    double sell_cJ = 0, sell_cU = 0, sell_cmu = 0;
 
     uint64_t* d_states = nullptr;  // packed occupations, LEX order
     double* d_dU = nullptr;        // sum_i n_i (n_i + 1)
@@ -91,6 +106,17 @@ int bh_fail(bh_ctx* ctx, int code, const std::string& msg);
         if (_rc != BH_OK) return _rc; \
     } while (0)
 #define BH_LAUNCHED(ctx) ((ctx)->launches++)
+// counted host<->device copies on the context's stream
+#define BH_H2D(ctx, dst, src, bytes)                                                                      \
+    do {                                                                                                  \
+        (ctx)->h2d_bytes += (int64_t)(bytes);                                                             \
+        BH_CUDA((ctx), cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, (ctx)->stream));    \
+    } while (0)
+#define BH_D2H(ctx, dst, src, bytes)                                                                      \
+    do {                                                                                                  \
+        (ctx)->d2h_bytes += (int64_t)(bytes);                                                             \
+        BH_CUDA((ctx), cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (ctx)->stream));    \
+    } while (0)
 
 // ---- internal entry points (defined across the .cu files) ----
 int bh_release_system(bh_ctx* ctx);
@@ -98,6 +124,7 @@ int bh_build_basis(bh_ctx* ctx);          // K1: states, dU
 int bh_build_hamiltonian(bh_ctx* ctx);    // K2: pattern, J values
 int bh_ensure_orderings(bh_ctx* ctx);     // tags, radix sort, permutations
 int bh_materialise_H(bh_ctx* ctx, double cJ, double cU, double cmu);
+int bh_materialise_sell(bh_ctx* ctx, double cJ, double cU, double cmu);  // builds the SELL copy on first use
 int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x_dev, double* y_dev,
                  double xscale_unused = 1.0);
 int bh_ensure_workspace(bh_ctx* ctx, int ncv);

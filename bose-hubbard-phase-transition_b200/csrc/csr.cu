@@ -100,7 +100,7 @@ static int exclusive_scan(bh_ctx* ctx, int64_t n, const int* d_in, int* d_out, i
     k_scan_add<<<nb, SCAN_THREADS, 0, ctx->stream>>>(n, d_out, d_bsum, d_bsum + nb);
     ctx->launches += 3;
     long long t = 0;
-    BH_CUDA(ctx, cudaMemcpyAsync(&t, d_bsum + nb, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    BH_D2H(ctx, &t, d_bsum + nb, sizeof(long long));
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_bsum);
     *total = t;
@@ -193,7 +193,8 @@ int bh_build_hamiltonian(bh_ctx* ctx)
     const int64_t D = ctx->D;
     int* d_len = nullptr;
     BH_CUDA(ctx, cudaMalloc(&d_len, sizeof(int) * D));
-    BH_CUDA(ctx, cudaMalloc(&ctx->d_rowptr, sizeof(int) * (D + 1)));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_rowptr, sizeof(int) * (D + 1 + 64)));  // slack: tiles copy whole 16-byte groups
+    BH_CUDA(ctx, cudaMemsetAsync(ctx->d_rowptr, 0, sizeof(int) * (D + 1 + 64), ctx->stream));
     k_row_count<<<nblocks(D, 256), 256, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, d_len);
     BH_LAUNCHED(ctx);
     int64_t total = 0;
@@ -256,6 +257,103 @@ int bh_materialise_H(bh_ctx* ctx, double cJ, double cU, double cmu)
     ctx->cur_cU = cU;
     ctx->cur_cmu = cmu;
     ctx->valH_valid = true;
+    return BH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SELL-32 copy of the stored matrix (sliced ELLPACK, C = 32, sigma = 1: rows keep their LEX order so that the
+// j-th entries of the 32 rows of a slice are mostly the same hop applied to neighbouring states and the
+// gathers of x fall into a few cache lines).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sell_sizes(int64_t D, int64_t nslices, const int* __restrict__ rowptr, int* __restrict__ sizes)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslices) return;
+    int w = 0;
+    for (int64_t r = s << 5; r < min((s << 5) + 32, D); ++r) w = max(w, rowptr[r + 1] - rowptr[r]);
+    sizes[s] = w << 5;
+}
+
+__global__ void k_sell_fill(int64_t D, int64_t nslices, const int* __restrict__ rowptr, const int* __restrict__ col,
+                            const double* __restrict__ valJ, const int* __restrict__ sptr, int* __restrict__ scol,
+                            double* __restrict__ sval, int* __restrict__ sdiag)
+{
+    const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= nslices) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (s << 5) + lane;
+    const int base = sptr[s], w = (sptr[s + 1] - base) >> 5;
+    int a = 0, len = 0;
+    if (r < D) {
+        a = rowptr[r];
+        len = rowptr[r + 1] - a;
+    }
+    const int self = (int)min(r, D - 1);
+    for (int j = 0; j < w; ++j) {
+        int c = self;
+        double v = 0.0;
+        if (j < len) {
+            c = col[a + j];
+            v = valJ[a + j];
+            if (c == (int)r) sdiag[r] = base + (j << 5) + lane;
+        }
+        scol[base + (j << 5) + lane] = c;
+        sval[base + (j << 5) + lane] = v;
+    }
+}
+
+__global__ void k_sell_scale(int64_t n, const double* __restrict__ valJ, double cJ, double* __restrict__ valH)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        valH[e] = __dmul_rn(valJ[e], cJ);
+}
+
+__global__ void k_sell_diag(int64_t D, int n, const int* __restrict__ sdiag, const double* __restrict__ valJ,
+                            const double* __restrict__ dU, double cJ, double cU, double cmu, double* __restrict__ valH)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= D) return;
+    const int p = sdiag[r];
+    const double a = __dadd_rn(__dmul_rn(valJ[p], cJ), __dmul_rn(dU[r], cU));
+    valH[p] = __dadd_rn(a, __dmul_rn(-(double)n, cmu));
+}
+
+int bh_materialise_sell(bh_ctx* ctx, double cJ, double cU, double cmu)
+{
+    const int64_t D = ctx->D;
+    if (!ctx->d_sell_ptr) {
+        const int64_t ns = (D + 31) / 32;
+        int* d_sizes = nullptr;
+        BH_CUDA(ctx, cudaMalloc(&d_sizes, sizeof(int) * ns));
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_ptr, sizeof(int) * (ns + 1)));
+        k_sell_sizes<<<nblocks(ns, 256), 256, 0, ctx->stream>>>(D, ns, ctx->d_rowptr, d_sizes);
+        BH_LAUNCHED(ctx);
+        int64_t total = 0;
+        BH_TRY(exclusive_scan(ctx, ns, d_sizes, ctx->d_sell_ptr, &total));
+        cudaFree(d_sizes);
+        if (total >= ((int64_t)1 << 31)) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "SELL copy has >= 2^31 entries");
+        ctx->sell_nslices = ns;
+        ctx->sell_entries = total;
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_col, sizeof(int) * total));
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_valJ, sizeof(double) * total));
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_valH, sizeof(double) * total));
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_diag, sizeof(int) * D));
+        k_sell_fill<<<nblocks(ns, 8), 256, 0, ctx->stream>>>(D, ns, ctx->d_rowptr, ctx->d_col, ctx->d_valJ, ctx->d_sell_ptr,
+                                                             ctx->d_sell_col, ctx->d_sell_valJ, ctx->d_sell_diag);
+        BH_LAUNCHED(ctx);
+        BH_CUDA(ctx, cudaGetLastError());
+        ctx->sell_valid = false;
+    }
+    if (ctx->sell_valid && ctx->sell_cJ == cJ && ctx->sell_cU == cU && ctx->sell_cmu == cmu) return BH_OK;
+    k_sell_scale<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->sell_entries, ctx->d_sell_valJ, cJ, ctx->d_sell_valH);
+    k_sell_diag<<<nblocks(D, 256), 256, 0, ctx->stream>>>(D, ctx->n, ctx->d_sell_diag, ctx->d_sell_valJ, ctx->d_dU, cJ, cU,
+                                                          cmu, ctx->d_sell_valH);
+    ctx->launches += 2;
+    BH_CUDA(ctx, cudaGetLastError());
+    ctx->sell_cJ = cJ;
+    ctx->sell_cU = cU;
+    ctx->sell_cmu = cmu;
+    ctx->sell_valid = true;
     return BH_OK;
 }
 
@@ -359,10 +457,10 @@ static int export_matrix(bh_ctx* ctx, int mode, double cJ, double cU, double cmu
     k_export_rows<<<nblocks(D, 128), 128, 0, ctx->stream>>>(D, ctx->n, ctx->d_rowptr, ctx->d_col, ctx->d_valJ, ctx->d_dU,
                                                              perm, inv, mode, cJ, cU, cmu, d_outer, d_inner, d_val);
     BH_LAUNCHED(ctx);
-    BH_CUDA(ctx, cudaMemcpyAsync(outer, d_outer, sizeof(int) * (D + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    BH_D2H(ctx, outer, d_outer, sizeof(int) * (D + 1));
     if (nnz) {
-        BH_CUDA(ctx, cudaMemcpyAsync(inner, d_inner, sizeof(int) * nnz, cudaMemcpyDeviceToHost, ctx->stream));
-        BH_CUDA(ctx, cudaMemcpyAsync(val, d_val, sizeof(double) * nnz, cudaMemcpyDeviceToHost, ctx->stream));
+        BH_D2H(ctx, inner, d_inner, sizeof(int) * nnz);
+        BH_D2H(ctx, val, d_val, sizeof(double) * nnz);
     }
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_len);
@@ -406,9 +504,9 @@ extern "C" int bh_term_csc(bh_ctx* ctx, int term, double coef, int order, int32_
     k_export_diag<<<nblocks(D + 1, 256), 256, 0, ctx->stream>>>(D, ctx->n, ctx->d_dU, perm, term, coef, d_outer, d_inner,
                                                                  d_val);
     BH_LAUNCHED(ctx);
-    BH_CUDA(ctx, cudaMemcpyAsync(outer, d_outer, sizeof(int) * (D + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    BH_CUDA(ctx, cudaMemcpyAsync(inner, d_inner, sizeof(int) * D, cudaMemcpyDeviceToHost, ctx->stream));
-    BH_CUDA(ctx, cudaMemcpyAsync(val, d_val, sizeof(double) * D, cudaMemcpyDeviceToHost, ctx->stream));
+    BH_D2H(ctx, outer, d_outer, sizeof(int) * (D + 1));
+    BH_D2H(ctx, inner, d_inner, sizeof(int) * D);
+    BH_D2H(ctx, val, d_val, sizeof(double) * D);
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_outer);
     cudaFree(d_inner);

@@ -7,7 +7,9 @@
 // and the tag ordering is a device radix sort on the raw bit patterns of the (positive) tags.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -56,6 +58,8 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
         return bh_fail(nullptr, BH_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     ctx->own_stream = true;
+    if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
+    if (const char* v = getenv("BH_HV_STAGES")) ctx->hv_stages = std::min(4, std::max(2, atoi(v)));
     *out = ctx;
     return BH_OK;
 }
@@ -77,6 +81,13 @@ int bh_release_system(bh_ctx* ctx)
     free_dev(ctx->d_valJ); ctx->d_valJ = nullptr;
     free_dev(ctx->d_diagpos); ctx->d_diagpos = nullptr;
     free_dev(ctx->d_valH); ctx->d_valH = nullptr;
+    free_dev(ctx->d_sell_ptr); ctx->d_sell_ptr = nullptr;
+    free_dev(ctx->d_sell_col); ctx->d_sell_col = nullptr;
+    free_dev(ctx->d_sell_valJ); ctx->d_sell_valJ = nullptr;
+    free_dev(ctx->d_sell_valH); ctx->d_sell_valH = nullptr;
+    free_dev(ctx->d_sell_diag); ctx->d_sell_diag = nullptr;
+    ctx->sell_valid = false;
+    ctx->sell_nslices = ctx->sell_entries = 0;
     free_dev(ctx->d_tags); ctx->d_tags = nullptr;
     free_dev(ctx->d_perm_tag); ctx->d_perm_tag = nullptr;
     free_dev(ctx->d_inv_tag); ctx->d_inv_tag = nullptr;
@@ -93,6 +104,8 @@ int bh_release_system(bh_ctx* ctx)
     ctx->h_pinned = nullptr;
     ctx->h_pinned_bytes = 0;
     ctx->ws_ncv = 0;
+    ctx->tile_cap = 0;
+    ctx->hv_smem_configured = 0;
     ctx->valH_valid = false;
     ctx->m = ctx->n = 0;
     ctx->D = 0;
@@ -127,6 +140,14 @@ extern "C" int bh_ctx_set_stream(bh_ctx* ctx, void* cuda_stream)
 }
 
 extern "C" int64_t bh_ctx_launch_count(const bh_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int bh_ctx_transfer_bytes(const bh_ctx* ctx, int64_t* h2d, int64_t* d2h)
+{
+    if (!ctx) return BH_ERR_ARG;
+    if (h2d) *h2d = ctx->h2d_bytes;
+    if (d2h) *d2h = ctx->d2h_bytes;
+    return BH_OK;
+}
 
 // ---- binomials (64-bit, exact) ----
 static int64_t binom64(int n, int k)
@@ -277,7 +298,7 @@ int bh_build_basis(bh_ctx* ctx)
     ctx->max_row = nb + 1;
 
     BH_CUDA(ctx, cudaMalloc(&ctx->d_tab, sizeof(BhTables)));
-    BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_tab, &t, sizeof(BhTables), cudaMemcpyHostToDevice, ctx->stream));
+    BH_H2D(ctx, ctx->d_tab, &t, sizeof(BhTables));
     BH_CUDA(ctx, cudaMalloc(&ctx->d_states, sizeof(uint64_t) * ctx->D));
     BH_CUDA(ctx, cudaMalloc(&ctx->d_dU, sizeof(double) * ctx->D));
     k_unrank<<<nblocks(ctx->D, 256), 256, 0, ctx->stream>>>(ctx->d_tab, ctx->D, ctx->d_states, ctx->d_dU);
@@ -400,9 +421,9 @@ extern "C" int bh_basis(bh_ctx* ctx, int order, double* tags, double* basis)
     if (basis) BH_CUDA(ctx, cudaMalloc(&d_b, sizeof(double) * D * ctx->m));
     k_export_basis<<<nblocks(D, 256), 256, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, perm, d_t, d_b);
     BH_LAUNCHED(ctx);
-    if (tags) BH_CUDA(ctx, cudaMemcpyAsync(tags, d_t, sizeof(double) * D, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tags) BH_D2H(ctx, tags, d_t, sizeof(double) * D);
     if (basis)
-        BH_CUDA(ctx, cudaMemcpyAsync(basis, d_b, sizeof(double) * D * ctx->m, cudaMemcpyDeviceToHost, ctx->stream));
+        BH_D2H(ctx, basis, d_b, sizeof(double) * D * ctx->m);
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     free_dev(d_t);
     free_dev(d_b);
@@ -424,10 +445,10 @@ extern "C" int bh_rank(bh_ctx* ctx, int order, const double* states, int64_t cou
     int* d_r = nullptr;
     BH_CUDA(ctx, cudaMalloc(&d_s, sizeof(double) * count * ctx->m));
     BH_CUDA(ctx, cudaMalloc(&d_r, sizeof(int) * count));
-    BH_CUDA(ctx, cudaMemcpyAsync(d_s, states, sizeof(double) * count * ctx->m, cudaMemcpyHostToDevice, ctx->stream));
+    BH_H2D(ctx, d_s, states, sizeof(double) * count * ctx->m);
     k_rank_states<<<nblocks(count, 256), 256, 0, ctx->stream>>>(ctx->d_tab, count, d_s, inv, d_r);
     BH_LAUNCHED(ctx);
-    BH_CUDA(ctx, cudaMemcpyAsync(ranks, d_r, sizeof(int) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    BH_D2H(ctx, ranks, d_r, sizeof(int) * count);
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_s);
     cudaFree(d_r);

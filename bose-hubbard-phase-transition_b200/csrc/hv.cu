@@ -11,6 +11,9 @@
 //     summation order as the reference's column-ordered scatter).  Algorithmic bytes: 12*nnz + 4*(D+1) + 16*D.
 // K4  stores no matrix: thread k re-derives row k from the packed state (8 B) with the O(1) incremental
 //     rank, so the HBM traffic is x, y, the packed states and the U-diagonal only.
+#include <algorithm>
+#include <cstdlib>
+
 #include "device_utils.cuh"
 
 static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
@@ -59,6 +62,172 @@ k_hv_csr(int64_t D, const int* __restrict__ rowptr, const int* __restrict__ col,
             y[r] = acc;
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, TMA-staged variant: every warp runs its own ring of STAGES shared-memory stages.  Lane 0 issues three
+// bulk async copies (cp.async.bulk -> UBLKCP) per 32-row tile -- the row-pointer slice, the column indices and
+// the values of the tile's contiguous entry range -- completing on an mbarrier, so the matrix stream is
+// prefetched STAGES-1 tiles ahead of the arithmetic and needs no registers.  The matrix is read exactly
+// once and marked evict-first in L2 so that it does not displace x (which the gathers re-use).
+// ---------------------------------------------------------------------------------------------
+#define HVT_WARPS 4
+#define HVT_BATCH 8
+#define HVT_RP 36  // row-pointer entries copied per tile (33 needed, 16-byte multiple)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(HVT_WARPS * 32)
+k_hv_csr_tma(int64_t D, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+             const double* __restrict__ x, double* __restrict__ y, int tile_cap)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t stage_bytes = (size_t)tile_cap * 12 + HVT_RP * 4;
+    unsigned char* wbase = smem_raw + (size_t)warp * STAGES * stage_bytes;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)HVT_WARPS * STAGES * stage_bytes) + warp * STAGES;
+    const int64_t ntiles = (D + 31) >> 5;
+    const int64_t wstride = (int64_t)gridDim.x * HVT_WARPS;
+    const int64_t wfirst = (int64_t)blockIdx.x * HVT_WARPS + warp;
+    uint64_t policy = 0;
+    if (lane == 0) {
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        for (int s = 0; s < STAGES; ++s) mbar_init(mbar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto issue = [&](int64_t tile, int stage) {  // lane 0 only
+        const int64_t r0 = tile << 5;
+        const int64_t r1 = min(r0 + 32, D);
+        const int e0 = __ldg(rowptr + r0), e1 = __ldg(rowptr + r1);
+        const int a0 = e0 & ~3, a1 = (e1 + 3) & ~3;
+        const uint32_t n = (uint32_t)(a1 - a0);
+        unsigned char* sb = wbase + (size_t)stage * stage_bytes;
+        mbar_expect_tx(mbar + stage, n * 12u + HVT_RP * 4u);
+        tma_load_1d(sb, val + a0, n * 8u, mbar + stage, policy);
+        tma_load_1d(sb + (size_t)tile_cap * 8, col + a0, n * 4u, mbar + stage, policy);
+        tma_load_1d(sb + (size_t)tile_cap * 12, rowptr + r0, HVT_RP * 4u, mbar + stage, policy);
+    };
+
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            const int64_t t = wfirst + (int64_t)s * wstride;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+    int k = 0;
+    for (int64_t tile = wfirst; tile < ntiles; tile += wstride, ++k) {
+        const int stage = k % STAGES;
+        mbar_wait(mbar + stage, (uint32_t)((k / STAGES) & 1));
+        unsigned char* sb = wbase + (size_t)stage * stage_bytes;
+        double* sval = reinterpret_cast<double*>(sb);
+        const int* scol = reinterpret_cast<const int*>(sb + (size_t)tile_cap * 8);
+        const int* srp = reinterpret_cast<const int*>(sb + (size_t)tile_cap * 12);
+        const int nvalid = (int)min((int64_t)32, D - (tile << 5));
+        const int e0 = srp[0], e1 = srp[nvalid];
+        const int a0 = e0 & ~3;
+        // phase 1: products in place of the values (entry-parallel, conflict-free shared accesses)
+        // (gathers issued in batches of HVT_BATCH per lane so that their L2 latency overlaps)
+        const int nE = e1 - a0;
+        for (int base = e0 - a0 + lane; base < nE; base += 32 * HVT_BATCH) {
+            int c[HVT_BATCH];
+            double xv[HVT_BATCH];
+#pragma unroll
+            for (int u = 0; u < HVT_BATCH; ++u) c[u] = (base + 32 * u < nE) ? scol[base + 32 * u] : -1;
+#pragma unroll
+            for (int u = 0; u < HVT_BATCH; ++u) xv[u] = (c[u] >= 0) ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < HVT_BATCH; ++u)
+                if (c[u] >= 0) sval[base + 32 * u] *= xv[u];
+        }
+        __syncwarp();
+        // phase 2: each lane adds up its own row in column order
+        if (lane < nvalid) {
+            double acc = 0.0;
+            for (int q = srp[lane] - a0; q < srp[lane + 1] - a0; ++q) acc += sval[q];
+            y[(tile << 5) + lane] = acc;
+        }
+        // the stage is rewritten by the async proxy next: order our generic-proxy accesses before it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const int64_t nt = tile + (int64_t)STAGES * wstride;
+            if (nt < ntiles) issue(nt, stage);
+        }
+    }
+}
+
+// max over 32-row tiles of the (16-byte aligned) entry count -> stage capacity of the TMA variant
+__global__ void k_tile_cap(int64_t D, const int* __restrict__ rowptr, int* __restrict__ out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r0 = t << 5;
+    if (r0 >= D) return;
+    const int64_t r1 = min(r0 + 32, D);
+    const int a0 = rowptr[r0] & ~3, a1 = (rowptr[r1] + 3) & ~3;
+    atomicMax(out, a1 - a0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, SELL-32 variant: one warp per slice of 32 rows, lane = row, entries column-major inside the slice.
+// Index / value loads are perfectly coalesced streaming loads (evict-first), no shared memory, full
+// occupancy; each lane accumulates its row in column order with FMAs.
+// ---------------------------------------------------------------------------------------------
+#define SELL_BATCH 8
+__global__ void __launch_bounds__(256)
+k_hv_sell(int64_t D, int64_t nslices, const int* __restrict__ sptr, const int* __restrict__ scol,
+          const double* __restrict__ sval, const double* __restrict__ x, double* __restrict__ y)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nslices; s += wstride) {
+        const int base = __ldg(sptr + s), end = __ldg(sptr + s + 1);
+        double acc = 0.0;
+        for (int p = base + lane; p < end; p += 32 * SELL_BATCH) {
+            int c[SELL_BATCH];
+            double v[SELL_BATCH], xv[SELL_BATCH];
+#pragma unroll
+            for (int u = 0; u < SELL_BATCH; ++u) {
+                const bool ok = p + 32 * u < end;
+                c[u] = ok ? __ldcs(scol + p + 32 * u) : -1;
+                v[u] = ok ? __ldcs(sval + p + 32 * u) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < SELL_BATCH; ++u) xv[u] = (c[u] >= 0) ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < SELL_BATCH; ++u) acc = fma(v[u], xv[u], acc);
+        }
+        const int64_t r = (s << 5) + lane;
+        if (r < D) y[r] = acc;
     }
 }
 
@@ -126,20 +295,54 @@ static hv_free_fn hv_free_kernel(int m)
 int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x, double* y, double)
 {
     const int64_t D = ctx->D;
-    if (kernel == BH_HV_STORED) {
-        BH_TRY(bh_materialise_H(ctx, cJ, cU, cmu));
-        const size_t smem = (size_t)HV_WARPS * 32 * ctx->max_row * sizeof(double);
-        static thread_local size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            BH_CUDA(ctx, cudaFuncSetAttribute(k_hv_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
-        const int64_t ntiles = (D + 31) / 32;
-        int grid = (int)std::min<int64_t>((ntiles + HV_WARPS - 1) / HV_WARPS, (int64_t)ctx->sm_count * per_sm);
-        k_hv_csr<<<grid, HV_WARPS * 32, smem, ctx->stream>>>(D, ctx->d_rowptr, ctx->d_col, ctx->d_valH, x, y,
-                                                             ctx->max_row);
+    if (kernel == BH_HV_STORED && ctx->hv_variant == 2) {
+        BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu));
+        const int64_t ns = ctx->sell_nslices;
+        const int grid = (int)std::min<int64_t>((ns + 7) / 8, (int64_t)ctx->sm_count * 8);
+        k_hv_sell<<<grid, 256, 0, ctx->stream>>>(D, ns, ctx->d_sell_ptr, ctx->d_sell_col, ctx->d_sell_valH, x, y);
         BH_LAUNCHED(ctx);
+    } else if (kernel == BH_HV_STORED) {
+        BH_TRY(bh_materialise_H(ctx, cJ, cU, cmu));
+        const int64_t ntiles = (D + 31) / 32;
+        if (ctx->hv_variant == 1) {
+            if (ctx->tile_cap == 0) {
+                int* d_cap = nullptr;
+                BH_CUDA(ctx, cudaMalloc(&d_cap, sizeof(int)));
+                BH_CUDA(ctx, cudaMemsetAsync(d_cap, 0, sizeof(int), ctx->stream));
+                k_tile_cap<<<nblocks(ntiles, 256), 256, 0, ctx->stream>>>(D, ctx->d_rowptr, d_cap);
+                BH_LAUNCHED(ctx);
+                int cap = 0;
+                BH_D2H(ctx, &cap, d_cap, sizeof(int));
+                BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                cudaFree(d_cap);
+                ctx->tile_cap = (cap + 3) & ~3;
+            }
+            const int stages = ctx->hv_stages;
+            const size_t stage_bytes = (size_t)ctx->tile_cap * 12 + HVT_RP * 4;
+            const size_t smem = (size_t)HVT_WARPS * stages * stage_bytes + HVT_WARPS * stages * 8;
+            if (smem > 227 * 1024) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "H.v tile does not fit in shared memory");
+            void (*fn)(int64_t, const int*, const int*, const double*, const double*, double*, int) =
+                stages == 2 ? k_hv_csr_tma<2> : stages == 3 ? k_hv_csr_tma<3> : k_hv_csr_tma<4>;
+            if (ctx->hv_smem_configured != smem) {
+                BH_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ctx->hv_smem_configured = smem;
+            }
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024)));
+            const int grid = (int)std::min<int64_t>((ntiles + HVT_WARPS - 1) / HVT_WARPS, (int64_t)ctx->sm_count * per_sm);
+            fn<<<grid, HVT_WARPS * 32, smem, ctx->stream>>>(D, ctx->d_rowptr, ctx->d_col, ctx->d_valH, x, y, ctx->tile_cap);
+            BH_LAUNCHED(ctx);
+        } else {
+            const size_t smem = (size_t)HV_WARPS * 32 * ctx->max_row * sizeof(double);
+            if (smem > 48 * 1024 && ctx->hv_smem_configured != smem) {
+                BH_CUDA(ctx, cudaFuncSetAttribute(k_hv_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ctx->hv_smem_configured = smem;
+            }
+            int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+            int grid = (int)std::min<int64_t>((ntiles + HV_WARPS - 1) / HV_WARPS, (int64_t)ctx->sm_count * per_sm);
+            k_hv_csr<<<grid, HV_WARPS * 32, smem, ctx->stream>>>(D, ctx->d_rowptr, ctx->d_col, ctx->d_valH, x, y,
+                                                                 ctx->max_row);
+            BH_LAUNCHED(ctx);
+        }
     } else if (kernel == BH_HV_MATRIX_FREE) {
         hv_free_fn fn = hv_free_kernel(ctx->m);
         int grid = (int)std::min<int64_t>(nblocks(D, 256), (int64_t)ctx->sm_count * 8);
@@ -168,11 +371,11 @@ extern "C" int bh_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, 
     BH_TRY(bh_ensure_staging(ctx));
     BH_TRY(bh_ensure_workspace(ctx, 0));
     const size_t bytes = sizeof(double) * ctx->D;
-    BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_y, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    BH_H2D(ctx, ctx->d_y, x, bytes);
     BH_TRY(bh_permute_vec(ctx, order, false, ctx->d_y, ctx->d_x));   // x_lex
     BH_TRY(bh_launch_hv(ctx, cJ, cU, cmu, kernel, ctx->d_x, ctx->d_w));
     BH_TRY(bh_permute_vec(ctx, order, true, ctx->d_w, ctx->d_y));    // y in `order`
-    BH_CUDA(ctx, cudaMemcpyAsync(y, ctx->d_y, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    BH_D2H(ctx, y, ctx->d_y, bytes);
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BH_OK;
 }

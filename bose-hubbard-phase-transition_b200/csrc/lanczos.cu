@@ -238,8 +238,8 @@ k_lincomb(int64_t D, int64_t ld, const double* __restrict__ V, int cnt, const do
 
 // K6: V[:, 0..k) <- V[:, 0..ncv) Y[:, 0..k), in place (a CTA owns CR rows: it reads all their ncv entries
 // into shared memory before it writes any of them).  Y is ncv x k column-major in global memory.
-#define CR 64
 #define CK 16
+template <int CR>
 __global__ void __launch_bounds__(256)
 k_compress(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, const double* __restrict__ Y)
 {
@@ -247,7 +247,7 @@ k_compress(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, const 
     double* vt = sm;                      // [ncv][CR]
     double* yc = sm + (size_t)ncv * CR;   // [CK][ncv]
     const int64_t r0 = (int64_t)blockIdx.x * CR;
-    const int rr = threadIdx.x % CR, cg = threadIdx.x / CR;  // 4 column groups
+    const int rr = threadIdx.x % CR, cg = threadIdx.x / CR;  // 256 / CR column groups
     for (int idx = threadIdx.x; idx < ncv * CR; idx += blockDim.x) {
         const int j = idx / CR, r = idx % CR;
         vt[idx] = (r0 + r < D) ? V[(int64_t)j * ld + r0 + r] : 0.0;
@@ -257,7 +257,7 @@ k_compress(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, const 
         __syncthreads();
         for (int idx = threadIdx.x; idx < nck * ncv; idx += blockDim.x) yc[idx] = Y[(size_t)c0 * ncv + idx];
         __syncthreads();
-        for (int l = cg; l < nck; l += 4) {
+        for (int l = cg; l < nck; l += 256 / CR) {
             const double* yl = yc + (size_t)l * ncv;
             double acc = 0.0;
             for (int j = 0; j < ncv; ++j) acc += vt[j * CR + rr] * yl[j];
@@ -320,9 +320,14 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
     std::vector<double> T, evals, Y;
     int from = 0, nconv = 0, iter = 0;
     double beta_last = 0.0;
-    const size_t compress_smem = sizeof(double) * ((size_t)ncv * CR + (size_t)CK * ncv);
-    if (compress_smem > 48 * 1024)
-        BH_CUDA(ctx, cudaFuncSetAttribute(k_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compress_smem));
+    const int CRsel = (ncv <= 160) ? 64 : 16;
+    const size_t compress_smem = sizeof(double) * ((size_t)ncv * CRsel + (size_t)CK * ncv);
+    if (compress_smem > 48 * 1024) {
+        if (CRsel == 64)
+            BH_CUDA(ctx, cudaFuncSetAttribute(k_compress<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compress_smem));
+        else
+            BH_CUDA(ctx, cudaFuncSetAttribute(k_compress<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compress_smem));
+    }
 
     for (;;) {
         for (int i = from; i < ncv; ++i) {
@@ -342,7 +347,7 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
             ctx->launches += 3 + 2 * passes;
         }
         BH_CUDA(ctx, cudaGetLastError());
-        BH_CUDA(ctx, cudaMemcpyAsync(h_scal.data(), scal, sizeof(double) * S_TOTAL, cudaMemcpyDeviceToHost, st));
+        BH_D2H(ctx, h_scal.data(), scal, sizeof(double) * S_TOTAL);
         BH_CUDA(ctx, cudaStreamSynchronize(st));
         if (h_scal[S_FLAG] != 0.0)
             return bh_fail(ctx, BH_ERR_NOCONV, "Lanczos breakdown (invariant subspace reached before ncv steps)");
@@ -377,8 +382,11 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
             knew = 2;
         if (knew > ncv - 1) knew = ncv - 1;
         // K6: V[:, 0..knew) <- V Y[:, 0..knew)
-        BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, Y.data(), sizeof(double) * (size_t)ncv * knew, cudaMemcpyHostToDevice, st));
-        k_compress<<<nblocks(D, CR), 256, compress_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
+        BH_H2D(ctx, ctx->d_small, Y.data(), sizeof(double) * (size_t)ncv * knew);
+        if (CRsel == 64)
+            k_compress<64><<<nblocks(D, 64), 256, compress_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
+        else
+            k_compress<16><<<nblocks(D, 16), 256, compress_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
         BH_LAUNCHED(ctx);
         theta.assign(evals.begin(), evals.begin() + knew);
         coup.resize(knew);
@@ -401,8 +409,7 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
 
 int bh_ritz_vector(bh_ctx* ctx, const BhSolve& s, int col, double* x_dev)
 {
-    BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, s.Y.data() + (size_t)col * s.ncv, sizeof(double) * s.ncv,
-                                 cudaMemcpyHostToDevice, ctx->stream));
+    BH_H2D(ctx, ctx->d_small, s.Y.data() + (size_t)col * s.ncv, sizeof(double) * s.ncv);
     const int G = (int)std::min<int64_t>(nblocks(ctx->D, VEC_THREADS), (int64_t)ctx->sm_count * 4);
     k_lincomb<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->D, ctx->ld, ctx->d_V, s.ncv, ctx->d_small, x_dev);
     BH_LAUNCHED(ctx);
@@ -426,8 +433,7 @@ extern "C" int bh_eigs(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, i
         for (int c = 0; c < nev; ++c) {
             BH_TRY(bh_ritz_vector(ctx, s, c, ctx->d_x));
             BH_TRY(bh_permute_vec(ctx, order, true, ctx->d_x, ctx->d_y));
-            BH_CUDA(ctx, cudaMemcpyAsync(evecs + (size_t)c * ctx->D, ctx->d_y, sizeof(double) * ctx->D,
-                                         cudaMemcpyDeviceToHost, ctx->stream));
+            BH_D2H(ctx, evecs + (size_t)c * ctx->D, ctx->d_y, sizeof(double) * ctx->D);
             BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
     }

@@ -109,7 +109,7 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
     k_spdm_reduce<<<1, m * m, 0, ctx->stream>>>(m, gx, d_part, 1.0 / (double)ncols, d_rho);
     ctx->launches += 2;
     BH_CUDA(ctx, cudaGetLastError());
-    BH_CUDA(ctx, cudaMemcpyAsync(rho_host, d_rho, sizeof(double) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    BH_D2H(ctx, rho_host, d_rho, sizeof(double) * m * m);
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_part);
     cudaFree(d_rho);
@@ -122,7 +122,7 @@ extern "C" int bh_spdm(bh_ctx* ctx, int order, const double* phi, int ncols, dou
     if (!phi || !rho || ncols < 1 || order < 0 || order > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_spdm: bad argument");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     BH_TRY(bh_ensure_staging(ctx));
-    BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_y, phi, sizeof(double) * ctx->D, cudaMemcpyHostToDevice, ctx->stream));
+    BH_H2D(ctx, ctx->d_y, phi, sizeof(double) * ctx->D);
     BH_TRY(bh_permute_vec(ctx, order, false, ctx->d_y, ctx->d_x));
     return bh_spdm_dev(ctx, ctx->d_x, ncols, rho);
 }

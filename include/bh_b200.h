@@ -52,6 +52,8 @@ const char* bh_last_error(const bh_ctx* ctx);
 int bh_ctx_set_stream(bh_ctx* ctx, void* cuda_stream);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t bh_ctx_launch_count(const bh_ctx* ctx);
+/* bytes this context has copied host->device and device->host since creation (bench.py's e2e accounting) */
+int bh_ctx_transfer_bytes(const bh_ctx* ctx, int64_t* h2d, int64_t* d2h);
 
 /* ---- geometry: replaces class Neighbours (include/neighbours.hpp:12-63, src/neighbours.cpp) ----- */
 /* Fill a CSR-style neighbour list: nbr_ptr[m+1], nbr_idx[nbr_ptr[m]].  Call with nbr_idx == NULL to get

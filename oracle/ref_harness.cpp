@@ -234,6 +234,39 @@ int main(int argc, char** argv)
                (t1 - t0) / (reps > 0 ? reps : 1), reps);
         return 0;
     }
+    if (cmd == "partial") {
+        // partial m n cJ cU cu maxit threads lattice
+        // Bounded sample of one grid point for the CPU baseline at sizes where a full solve takes minutes:
+        // `threads` concurrent copies (one per core, as the sweep's OpenMP loop would run them) of the
+        // reference solver call of src/operator.cpp:22-26 on the same H, stopped after `maxit` restarts.
+        int m = atoi(argv[2]), n = atoi(argv[3]);
+        double cJ = atof(argv[4]), cU = atof(argv[5]), cu = atof(argv[6]);
+        int maxit = atoi(argv[7]), threads = atoi(argv[8]);
+        std::string lat = argv[9];
+        double tb0 = now();
+        Terms t = build_terms(m, n, lat);
+        double tb1 = now();
+        Eigen::SparseMatrix<double> Hf = t.JH * cJ;
+        Eigen::SparseMatrix<double> H = Hf + t.UH * cU + t.uH * cu;
+        if (threads < 1) threads = omp_get_max_threads();
+        std::vector<long> ops(threads), its(threads), conv(threads);
+        double t0 = now();
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+        for (int c = 0; c < threads; ++c) {
+            Spectra::SparseGenMatProd<double> op(H);
+            Spectra::GenEigsSolver<Spectra::SparseGenMatProd<double>> eigs(op, 20, 41);
+            eigs.init();
+            int nconv = eigs.compute(Spectra::SortRule::SmallestReal, maxit, 1e-10, Spectra::SortRule::SmallestReal);
+            ops[c] = eigs.num_operations();
+            its[c] = eigs.num_iterations();
+            conv[c] = nconv;
+        }
+        double t1 = now();
+        printf("{\"D\": %ld, \"nnz\": %ld, \"threads\": %d, \"seconds\": %.6f, \"setup_seconds\": %.6f, \"nmatvec\": %ld, "
+               "\"nrestart\": %ld, \"nconv\": %ld}\n",
+               (long)H.rows(), (long)H.nonZeros(), threads, t1 - t0, tb1 - tb0, ops[0], its[0], conv[0]);
+        return 0;
+    }
     if (cmd == "points") {
         // points m n fixed cfix p1min p2min step n1 n2 threads lattice out
         // A (sub)grid of the sweep, body identical to analysis.cpp:302-343, OpenMP over points with

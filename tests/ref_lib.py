@@ -81,6 +81,11 @@ def points(m, n, fixed, cfix, p1min, p2min, step, n1, n2, threads=0, lattice="ch
     return r, info
 
 
+def partial(m, n, cJ, cU, cu, maxit, threads=0, lattice="chain", timeout=7200):
+    info, _ = _run(HARNESS, ["partial", m, n, cJ, cU, cu, maxit, threads, lattice], [], timeout=timeout)
+    return info
+
+
 def cli_phase(args, threads=None, timeout=7200):
     """Run the patched reference CLI in a scratch dir; returns the text of phase.txt."""
     with tempfile.TemporaryDirectory() as td:
