@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libbh_b200.so")
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOCONV, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 LEX, TAG_SORTED, REF_SCATTER = 0, 1, 2
 TERM_J, TERM_U, TERM_MU = 0, 1, 2
-HV_STORED, HV_MATRIX_FREE = 0, 1
+HV_STORED, HV_MATRIX_FREE, HV_USER = 0, 1, 2
 
 # every symbol include/bh_b200.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [
@@ -23,7 +23,7 @@ SYMBOLS = [
     "bh_neighbours_chain", "bh_neighbours_rect", "bh_dimension", "bh_setup", "bh_basis", "bh_rank",
     "bh_term_nnz", "bh_term_csc", "bh_hamiltonian_nnz", "bh_hamiltonian_csc", "bh_hv", "bh_hv_dev", "bh_eigs",
     "bh_spdm", "bh_gap_ratios", "bh_condensate_fraction", "bh_coherence", "bh_point", "bh_points",
-    "bh_lcg_fill_dev", "bh_hv_algorithmic_bytes",
+    "bh_lcg_fill_dev", "bh_hv_algorithmic_bytes", "bh_load_matrix",
 ]
 
 
@@ -81,6 +81,7 @@ def load():
     L.bh_coherence.argtypes = [C.c_int, vp, dp]
     L.bh_point.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, C.POINTER(EigsInfo)]
     L.bh_points.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
+    L.bh_load_matrix.argtypes = [vp, C.c_int64, vp, vp, vp]
     L.bh_lcg_fill_dev.argtypes = [vp, vp, C.c_int64]
     L.bh_hv_algorithmic_bytes.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
     _lib = L
@@ -185,6 +186,16 @@ class Context:
         idx = np.ascontiguousarray(idx, dtype=np.int32)
         self._check(self.L.bh_setup(self.h, m, n, _ptr(ptr), _ptr(idx)))
         self.m, self.n, self.D = m, n, dimension(m, n)
+        return self
+
+    def load_matrix(self, outer, inner, val):
+        outer = np.ascontiguousarray(outer, dtype=np.int32)
+        inner = np.ascontiguousarray(inner, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        D = len(outer) - 1
+        self._check(self.L.bh_load_matrix(self.h, D, _ptr(outer), _ptr(inner), _ptr(val)))
+        self.m = self.n = 0
+        self.D = D
         return self
 
     def basis(self, order=TAG_SORTED):

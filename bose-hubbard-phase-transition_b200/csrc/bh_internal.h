@@ -38,6 +38,7 @@ struct bh_ctx {
     int64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied across PCIe by this context
 
     // system
+    bool user_matrix = false;  // true after bh_load_matrix: no Fock basis, only the SELL copy of the given matrix
     int m = 0, n = 0;
     int64_t D = 0;
     int64_t ld = 0;  // padded vector length (multiple of 32 doubles)

@@ -318,32 +318,38 @@ __global__ void k_sell_diag(int64_t D, int n, const int* __restrict__ sdiag, con
     valH[p] = __dadd_rn(a, __dmul_rn(-(double)n, cmu));
 }
 
+static int build_sell(bh_ctx* ctx)
+{
+    const int64_t D = ctx->D;
+    const int64_t ns = (D + 31) / 32;
+    int* d_sizes = nullptr;
+    BH_CUDA(ctx, cudaMalloc(&d_sizes, sizeof(int) * ns));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_ptr, sizeof(int) * (ns + 1)));
+    k_sell_sizes<<<nblocks(ns, 256), 256, 0, ctx->stream>>>(D, ns, ctx->d_rowptr, d_sizes);
+    BH_LAUNCHED(ctx);
+    int64_t total = 0;
+    BH_TRY(exclusive_scan(ctx, ns, d_sizes, ctx->d_sell_ptr, &total));
+    cudaFree(d_sizes);
+    if (total >= ((int64_t)1 << 31)) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "SELL copy has >= 2^31 entries");
+    ctx->sell_nslices = ns;
+    ctx->sell_entries = total;
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_col, sizeof(int) * std::max<int64_t>(total, 1)));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_valJ, sizeof(double) * std::max<int64_t>(total, 1)));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_valH, sizeof(double) * std::max<int64_t>(total, 1)));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_diag, sizeof(int) * D));
+    BH_CUDA(ctx, cudaMemsetAsync(ctx->d_sell_diag, 0, sizeof(int) * D, ctx->stream));
+    k_sell_fill<<<nblocks(ns, 8), 256, 0, ctx->stream>>>(D, ns, ctx->d_rowptr, ctx->d_col, ctx->d_valJ, ctx->d_sell_ptr,
+                                                         ctx->d_sell_col, ctx->d_sell_valJ, ctx->d_sell_diag);
+    BH_LAUNCHED(ctx);
+    BH_CUDA(ctx, cudaGetLastError());
+    ctx->sell_valid = false;
+    return BH_OK;
+}
+
 int bh_materialise_sell(bh_ctx* ctx, double cJ, double cU, double cmu)
 {
     const int64_t D = ctx->D;
-    if (!ctx->d_sell_ptr) {
-        const int64_t ns = (D + 31) / 32;
-        int* d_sizes = nullptr;
-        BH_CUDA(ctx, cudaMalloc(&d_sizes, sizeof(int) * ns));
-        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_ptr, sizeof(int) * (ns + 1)));
-        k_sell_sizes<<<nblocks(ns, 256), 256, 0, ctx->stream>>>(D, ns, ctx->d_rowptr, d_sizes);
-        BH_LAUNCHED(ctx);
-        int64_t total = 0;
-        BH_TRY(exclusive_scan(ctx, ns, d_sizes, ctx->d_sell_ptr, &total));
-        cudaFree(d_sizes);
-        if (total >= ((int64_t)1 << 31)) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "SELL copy has >= 2^31 entries");
-        ctx->sell_nslices = ns;
-        ctx->sell_entries = total;
-        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_col, sizeof(int) * total));
-        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_valJ, sizeof(double) * total));
-        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_valH, sizeof(double) * total));
-        BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_diag, sizeof(int) * D));
-        k_sell_fill<<<nblocks(ns, 8), 256, 0, ctx->stream>>>(D, ns, ctx->d_rowptr, ctx->d_col, ctx->d_valJ, ctx->d_sell_ptr,
-                                                             ctx->d_sell_col, ctx->d_sell_valJ, ctx->d_sell_diag);
-        BH_LAUNCHED(ctx);
-        BH_CUDA(ctx, cudaGetLastError());
-        ctx->sell_valid = false;
-    }
+    if (!ctx->d_sell_ptr) BH_TRY(build_sell(ctx));
     if (ctx->sell_valid && ctx->sell_cJ == cJ && ctx->sell_cU == cU && ctx->sell_cmu == cmu) return BH_OK;
     k_sell_scale<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->sell_entries, ctx->d_sell_valJ, cJ, ctx->d_sell_valH);
     k_sell_diag<<<nblocks(D, 256), 256, 0, ctx->stream>>>(D, ctx->n, ctx->d_sell_diag, ctx->d_sell_valJ, ctx->d_dU, cJ, cU,
@@ -472,7 +478,7 @@ static int export_matrix(bh_ctx* ctx, int mode, double cJ, double cU, double cmu
 
 extern "C" int bh_term_nnz(bh_ctx* ctx, int term, int64_t* nnz)
 {
-    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_term_nnz: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_term_nnz: call bh_setup first");
     if (!nnz || term < 0 || term > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_term_nnz: bad argument");
     *nnz = (term == BH_TERM_J) ? ctx->nnzJ : ctx->D;
     return BH_OK;
@@ -480,7 +486,7 @@ extern "C" int bh_term_nnz(bh_ctx* ctx, int term, int64_t* nnz)
 
 extern "C" int bh_hamiltonian_nnz(bh_ctx* ctx, int64_t* nnz)
 {
-    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_hamiltonian_nnz: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_hamiltonian_nnz: call bh_setup first");
     if (!nnz) return bh_fail(ctx, BH_ERR_ARG, "bh_hamiltonian_nnz: bad argument");
     *nnz = ctx->nnzH;
     return BH_OK;
@@ -488,7 +494,7 @@ extern "C" int bh_hamiltonian_nnz(bh_ctx* ctx, int64_t* nnz)
 
 extern "C" int bh_term_csc(bh_ctx* ctx, int term, double coef, int order, int32_t* outer, int32_t* inner, double* val)
 {
-    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_term_csc: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_term_csc: call bh_setup first");
     if (term < 0 || term > 2 || order < 0 || order > 2 || !outer || !inner || !val)
         return bh_fail(ctx, BH_ERR_ARG, "bh_term_csc: bad argument");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -517,8 +523,44 @@ extern "C" int bh_term_csc(bh_ctx* ctx, int term, double coef, int order, int32_
 extern "C" int bh_hamiltonian_csc(bh_ctx* ctx, double cJ, double cU, double cmu, int order, int32_t* outer,
                                   int32_t* inner, double* val)
 {
-    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_hamiltonian_csc: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_hamiltonian_csc: call bh_setup first");
     if (order < 0 || order > 2 || !outer || !inner || !val) return bh_fail(ctx, BH_ERR_ARG, "bh_hamiltonian_csc: bad argument");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     return export_matrix(ctx, EXPORT_HSUM, cJ, cU, cmu, order, outer, inner, val);
+}
+
+// ---------------------------------------------------------------------------------------------
+// user matrix (the literal Op::IRLM_eigen(SparseMatrix O, ..) seam, reference src/operator.cpp:22-33)
+// ---------------------------------------------------------------------------------------------
+extern "C" int bh_load_matrix(bh_ctx* ctx, int64_t D, const int32_t* outer, const int32_t* inner, const double* val)
+{
+    if (!ctx) return BH_ERR_ARG;
+    if (D < 1 || D >= ((int64_t)1 << 31) || !outer || !inner || !val) return bh_fail(ctx, BH_ERR_ARG, "bh_load_matrix: bad argument");
+    BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nnz = outer[D];
+    if (outer[0] != 0 || nnz < 0) return bh_fail(ctx, BH_ERR_ARG, "bh_load_matrix: outer index array must start at 0");
+    bh_release_system(ctx);
+    ctx->user_matrix = true;
+    ctx->D = D;
+    ctx->ld = (D + 31) / 32 * 32;
+    ctx->nnzH = nnz;
+    ctx->nnzJ = nnz;
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_rowptr, sizeof(int) * (D + 1 + 64)));
+    BH_CUDA(ctx, cudaMemsetAsync(ctx->d_rowptr, 0, sizeof(int) * (D + 1 + 64), ctx->stream));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_col, sizeof(int) * (nnz + 8)));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_valJ, sizeof(double) * (nnz + 8)));
+    BH_H2D(ctx, ctx->d_rowptr, outer, sizeof(int) * (D + 1));
+    if (nnz) {
+        BH_H2D(ctx, ctx->d_col, inner, sizeof(int) * nnz);
+        BH_H2D(ctx, ctx->d_valJ, val, sizeof(double) * nnz);
+    }
+    BH_TRY(build_sell(ctx));
+    BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_sell_valH, ctx->d_sell_valJ, sizeof(double) * ctx->sell_entries,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->sell_valid = true;
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // the CSR staging copy is no longer needed
+    cudaFree(ctx->d_col); ctx->d_col = nullptr;
+    cudaFree(ctx->d_valJ); ctx->d_valJ = nullptr;
+    return BH_OK;
 }

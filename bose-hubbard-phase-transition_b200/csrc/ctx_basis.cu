@@ -109,6 +109,7 @@ int bh_release_system(bh_ctx* ctx)
     ctx->valH_valid = false;
     ctx->m = ctx->n = 0;
     ctx->D = 0;
+    ctx->user_matrix = false;
     return BH_OK;
 }
 
@@ -352,6 +353,7 @@ int bh_permute_vec(bh_ctx* ctx, int order, bool to_order, const double* src, dou
             BH_CUDA(ctx, cudaMemcpyAsync(dst, src, sizeof(double) * ctx->D, cudaMemcpyDeviceToDevice, ctx->stream));
         return BH_OK;
     }
+    if (ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "a loaded matrix has only its own ordering (BH_ORDER_LEX)");
     BH_TRY(bh_ensure_orderings(ctx));
     // to_order: dst[pos] = src[lex(pos)];  from order: dst[lex] = src[pos(lex)]
     const int* idx = to_order ? perm_of(ctx, order) : inv_of(ctx, order);
@@ -407,7 +409,7 @@ int bh_ensure_staging(bh_ctx* ctx)
 
 extern "C" int bh_basis(bh_ctx* ctx, int order, double* tags, double* basis)
 {
-    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_basis: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_basis: call bh_setup first");
     if (order < 0 || order > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_basis: bad order");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t D = ctx->D;
@@ -432,7 +434,7 @@ extern "C" int bh_basis(bh_ctx* ctx, int order, double* tags, double* basis)
 
 extern "C" int bh_rank(bh_ctx* ctx, int order, const double* states, int64_t count, int32_t* ranks)
 {
-    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_rank: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_rank: call bh_setup first");
     if (order < 0 || order > 2 || !states || !ranks || count < 0) return bh_fail(ctx, BH_ERR_ARG, "bh_rank: bad argument");
     if (count == 0) return BH_OK;
     BH_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -295,8 +295,10 @@ static hv_free_fn hv_free_kernel(int m)
 int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x, double* y, double)
 {
     const int64_t D = ctx->D;
-    if (kernel == BH_HV_STORED && ctx->hv_variant == 2) {
-        BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu));
+    if (ctx->user_matrix != (kernel == BH_HV_USER))
+        return bh_fail(ctx, BH_ERR_STATE, "kernel BH_HV_USER needs bh_load_matrix, the other kernels need bh_setup");
+    if (kernel == BH_HV_USER || (kernel == BH_HV_STORED && ctx->hv_variant == 2)) {
+        if (kernel == BH_HV_STORED) BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu));
         const int64_t ns = ctx->sell_nslices;
         const int grid = (int)std::min<int64_t>((ns + 7) / 8, (int64_t)ctx->sm_count * 8);
         k_hv_sell<<<grid, 256, 0, ctx->stream>>>(D, ns, ctx->d_sell_ptr, ctx->d_sell_col, ctx->d_sell_valH, x, y);
@@ -383,7 +385,7 @@ extern "C" int bh_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, 
 extern "C" int bh_hv_algorithmic_bytes(bh_ctx* ctx, int kernel, int64_t* bytes)
 {
     if (!ctx || !ctx->D || !bytes) return bh_fail(ctx, BH_ERR_STATE, "bh_hv_algorithmic_bytes: call bh_setup first");
-    if (kernel == BH_HV_STORED)
+    if (kernel == BH_HV_STORED || kernel == BH_HV_USER)
         *bytes = 12 * ctx->nnzH + 4 * (ctx->D + 1) + 16 * ctx->D;
     else
         *bytes = 16 * ctx->D;

@@ -118,7 +118,7 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
 
 extern "C" int bh_spdm(bh_ctx* ctx, int order, const double* phi, int ncols, double* rho)
 {
-    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_spdm: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_spdm: call bh_setup first");
     if (!phi || !rho || ncols < 1 || order < 0 || order > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_spdm: bad argument");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     BH_TRY(bh_ensure_staging(ctx));
@@ -173,7 +173,7 @@ extern "C" int bh_coherence(int m, const double* rho, double* out)
 extern "C" int bh_point(bh_ctx* ctx, double cJ, double cU, double cmu, int nb_eigen, int kernel, double* out3,
                         double* evals, double* rho, bh_eigs_info* info)
 {
-    if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_point: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_point: call bh_setup first");
     if (!out3 || nb_eigen < 3) return bh_fail(ctx, BH_ERR_ARG, "bh_point: bad argument");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     BhSolve s;

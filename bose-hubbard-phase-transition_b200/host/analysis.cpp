@@ -1,0 +1,194 @@
+// analysis.cpp -- the (J, U, mu) sweep driver on top of the C ABI.
+//
+// Mirrors Analysis::exact_parameters / calculate_and_save (reference src/analysis.cpp:207-427): same range
+// plumbing (including the parameter mix-up of :242-256), same grid-size arithmetic (:281-282),
+// same result indexing (:341), same variance-restart rule (:364-380) and the same phase.txt format (:269-274,
+// :384-387).  Grid points are independent, so instead of an OpenMP team the points are pulled from a shared
+// counter by one host thread per GPU, each owning a bh_ctx (no collective on the data path).
+#include "analysis.hpp"
+
+#include <atomic>
+#include <cmath>
+#include <cuda_runtime_api.h>
+#include <exception>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <mutex>
+#include <numeric>
+#include <stdexcept>
+#include <thread>
+
+#include "../../include/bh_b200.h"
+#include "neighbours.hpp"
+#include "resource.hpp"
+
+namespace {
+
+struct Grid {
+    std::string fixed;
+    double fixed_value;
+    double p1_min, p1_max, p2_min, p2_max, step1, step2;
+    int num1, num2;
+};
+
+// coefficient triple (cJ, cU, cmu) of a grid point, by sweep mode (src/analysis.cpp:245-256)
+void coefficients(const Grid& g, double p1, double p2, double& cJ, double& cU, double& cmu)
+{
+    if (g.fixed == "J") {          // H = JH*J + UH*p1 + uH*p2
+        cJ = g.fixed_value; cU = p1; cmu = p2;
+    } else if (g.fixed == "U") {   // H = UH*U + JH*p1 + uH*p2
+        cU = g.fixed_value; cJ = p1; cmu = p2;
+    } else {                       // H = uH*mu + JH*p1 + UH*p2
+        cmu = g.fixed_value; cJ = p1; cU = p2;
+    }
+}
+
+std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::vector<std::vector<int>>& nei, const Grid& g,
+                                                     const Analysis::ExactOptions& opt)
+{
+    std::ofstream file(opt.output);
+    file << g.fixed << " " << g.fixed_value << std::endl;
+
+    int nb_eigen = opt.nb_eigen;
+    const int total = g.num1 * g.num2;
+    std::vector<Analysis::SweepPoint> res(total, Analysis::SweepPoint{0, 0, 0, 0, 0});
+
+    // neighbour list in the C ABI's CSR form
+    std::vector<int> nbr_ptr(m + 1, 0), nbr_idx;
+    for (int i = 0; i < m; ++i) {
+        nbr_ptr[i + 1] = nbr_ptr[i] + static_cast<int>(nei[i].size());
+        nbr_idx.insert(nbr_idx.end(), nei[i].begin(), nei[i].end());
+    }
+    if (nbr_idx.empty()) nbr_idx.push_back(0);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        throw std::runtime_error("no CUDA device: the exact path has no CPU fallback");
+    const int ngpu = (opt.gpus > 0) ? std::min(opt.gpus, ndev) : ndev;
+
+    std::vector<bh_ctx*> ctxs(ngpu, nullptr);
+    for (int d = 0; d < ngpu; ++d) {
+        if (bh_ctx_create(d, &ctxs[d]) != BH_OK) throw std::runtime_error(bh_last_error(nullptr));
+        if (bh_setup(ctxs[d], m, n, nbr_ptr.data(), nbr_idx.data()) != BH_OK) {
+            std::string msg = bh_last_error(ctxs[d]);
+            for (bh_ctx* c : ctxs) bh_ctx_destroy(c);
+            throw std::runtime_error(msg);
+        }
+    }
+
+    const double variance_threshold_percent = 1e-8;  // src/analysis.cpp:298
+    const int bar_width = 100;
+    std::exception_ptr failure;
+    std::mutex mtx;
+
+    while (true) {
+        std::atomic<int> next(0), done(0);
+        auto worker = [&](int d) {
+            try {
+                for (;;) {
+                    const int t = next.fetch_add(1);
+                    if (t >= total) break;
+                    const int i = t / g.num2, j = t % g.num2;
+                    const double p1 = g.p1_min + i * g.step1;
+                    const double p2 = g.p2_min + j * g.step2;
+                    double cJ, cU, cmu, out3[3];
+                    coefficients(g, p1, p2, cJ, cU, cmu);
+                    const int rc = bh_point(ctxs[d], cJ, cU, cmu, nb_eigen, opt.kernel, out3, nullptr, nullptr, nullptr);
+                    if (rc == BH_ERR_ARG) throw std::invalid_argument(bh_last_error(ctxs[d]));
+                    if (rc != BH_OK) throw std::runtime_error(bh_last_error(ctxs[d]));
+                    const int index = i * g.num1 + j;  // src/analysis.cpp:341 (sic)
+                    std::lock_guard<std::mutex> lk(mtx);
+                    if (index >= 0 && index < total) res[index] = Analysis::SweepPoint{p1, p2, out3[0], out3[1], out3[2]};
+                    const int c = ++done;
+                    if (opt.progress) {
+                        const int progress = (c * bar_width) / total;
+                        std::cout << "\rProgress: [" << std::string(progress, '#') << std::string(bar_width - progress, ' ') << "] "
+                                  << std::setw(3) << (c * 100) / total << "% " << std::flush;
+                    }
+                }
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(mtx);
+                if (!failure) failure = std::current_exception();
+                next.store(total);
+            }
+        };
+        std::vector<std::thread> team;
+        for (int d = 0; d < ngpu; ++d) team.emplace_back(worker, d);
+        for (auto& th : team) th.join();
+        if (failure) break;
+
+        // src/analysis.cpp:364-380
+        double mean = 0.0;
+        for (const auto& p : res) mean += p.gap_ratio;
+        mean /= res.size();
+        double variance = 0.0;
+        for (const auto& p : res) variance += (p.gap_ratio - mean) * (p.gap_ratio - mean);
+        variance /= res.size();
+        if (variance > variance_threshold_percent * mean) break;
+        nb_eigen += 5;
+    }
+    for (bh_ctx* c : ctxs) bh_ctx_destroy(c);
+    if (failure) std::rethrow_exception(failure);
+
+    for (const auto& p : res)
+        file << p.param1 << " " << p.param2 << " " << p.gap_ratio << " " << p.condensate_fraction << " " << p.coherence << std::endl;
+    file.close();
+    return res;
+}
+
+}  // namespace
+
+std::vector<Analysis::SweepPoint> Analysis::exact_parameters(int m, int n, double J, double U, double mu, double s, double r,
+                                                             std::string fixed_param, const ExactOptions& opt)
+{
+    const double eps = std::numeric_limits<double>::epsilon();
+    if (std::abs(J - 0.0) < eps && std::abs(U - 0.0) < eps && std::abs(mu - 0.0) < eps) {
+        std::cerr << "Error: At least one of the parameters J, U, mu must be different from zero." << std::endl;
+        return {};
+    }
+    Resource::timer();
+
+    Neighbours neighbours(m);
+    if (opt.lx > 0)
+        neighbours.rect_neighbours(opt.lx, opt.ly > 0 ? opt.ly : 1, opt.lz > 0 ? opt.lz : 1, opt.closed);
+    else
+        neighbours.chain_neighbours(opt.closed);
+    const std::vector<std::vector<int>> nei = neighbours.getNeighbours();
+
+    // src/analysis.cpp:242-256
+    const double J_min = J, J_max = J + r, mu_min = mu, mu_max = mu + r, U_min = U, U_max = U + r;
+    Grid g;
+    g.fixed = fixed_param;
+    g.step1 = g.step2 = s;
+    if (fixed_param == "J") {
+        g.fixed_value = J; g.p1_min = J_min; g.p1_max = J_max; g.p2_min = mu_min; g.p2_max = mu_max;
+    } else if (fixed_param == "U") {
+        g.fixed_value = U; g.p1_min = J_min; g.p1_max = J_max; g.p2_min = U_min; g.p2_max = U_max;
+    } else {
+        g.fixed_value = mu; g.p1_min = J_min; g.p1_max = J_max; g.p2_min = mu_min; g.p2_max = mu_max;
+    }
+    // src/analysis.cpp:281-282, evaluated in double exactly as written
+    g.num1 = static_cast<int>((g.p1_max - g.p1_min) / g.step1) + 1;
+    g.num2 = static_cast<int>((g.p2_max - g.p2_min) / g.step2) + 1;
+
+    std::vector<SweepPoint> rows = calculate_and_save(m, n, nei, g, opt);
+
+    std::cout << std::endl;
+    Resource::timer();
+    Resource::get_memory_usage(true);
+    return rows;
+}
+
+void Analysis::exact_parameters(int m, int n, double J, double U, double mu, double s, double r, std::string fixed_param)
+{
+    ExactOptions opt;
+    exact_parameters(m, n, J, U, mu, s, r, fixed_param, opt);
+}
+
+void Analysis::mean_field_parameters(int, int)
+{
+    std::cerr << "The mean-field calculation is outside the accelerated exact-diagonalisation path; "
+                 "use the reference program for -t mean." << std::endl;
+}

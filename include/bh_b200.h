@@ -41,7 +41,7 @@ enum { BH_OK = 0, BH_ERR_ARG = -1, BH_ERR_CUDA = -2, BH_ERR_STATE = -3, BH_ERR_N
 enum { BH_ORDER_LEX = 0, BH_ORDER_TAG_SORTED = 1, BH_ORDER_REF_SCATTER = 2 };
 enum { BH_TERM_J = 0, BH_TERM_U = 1, BH_TERM_MU = 2 };
 /* H.v kernels: stored CSR (K3) or matrix-free on-the-fly (K4) */
-enum { BH_HV_STORED = 0, BH_HV_MATRIX_FREE = 1 };
+enum { BH_HV_STORED = 0, BH_HV_MATRIX_FREE = 1, BH_HV_USER = 2 /* matrix loaded with bh_load_matrix */ };
 
 /* ---- context ------------------------------------------------------------------------------- */
 int bh_ctx_create(int device, bh_ctx** ctx);
@@ -103,6 +103,13 @@ typedef struct bh_eigs_info {
  * nev/ncv violate Spectra's constructor checks (nev + 2 <= ncv <= D for the general solver). */
 int bh_eigs(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
             int order, double* evals, double* evecs, bh_eigs_info* info);
+
+/* ---- generic operator: the literal Op::IRLM_eigen(Eigen::SparseMatrix<double> O, ...) seam -------- */
+/* Load any real symmetric sparse matrix (compressed columns = compressed rows, ascending inner indices, the
+ * arrays of an Eigen::SparseMatrix<double>) into the context; it replaces the context's system.  The matrix is
+ * copied to the device and converted to the SELL-32 layout there.  Afterwards bh_eigs / bh_hv with
+ * kernel = BH_HV_USER and order = BH_ORDER_LEX (the matrix's own ordering) operate on it; cJ/cU/cmu are ignored. */
+int bh_load_matrix(bh_ctx* ctx, int64_t D, const int32_t* outer, const int32_t* inner, const double* val);
 
 /* ---- observables: replaces Analysis::SPDM/braket/coherence/gap_ratios (src/analysis.cpp:433-594) */
 /* rho[m*m] column-major from a state vector phi (host, `order`), divided by ncols (the reference divides

@@ -1,0 +1,116 @@
+"""CPU: the oracle (oracle/bh_oracle.cpp) against the golden fixtures generated from the real patched
+reference (tests/golden/make_golden.py).  This is what pins the oracle; see also test_oracle_vs_ref.py."""
+import os
+
+import numpy as np
+import pytest
+
+from checksums import checksum_basis, checksum_csc
+
+import oracle_lib as O
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.npz"))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+@pytest.mark.parametrize("m,n", [(3, 2), (4, 4), (5, 3)])
+@pytest.mark.parametrize("order,name", [(O.TAG_SORTED, "sorted"), (O.REF_SCATTER, "scatter")])
+def test_basis_bit_exact(m, n, order, name):
+    t, b = O.basis(m, n, order)
+    assert (bits(t) == bits(G[f"basis_{m}_{n}_{name}_tags"])).all()
+    assert (b == G[f"basis_{m}_{n}_{name}_states"]).all()
+
+
+@pytest.mark.parametrize("m,n", [(6, 6), (8, 8), (10, 10)])
+@pytest.mark.parametrize("order,name", [(O.TAG_SORTED, "sorted"), (O.REF_SCATTER, "scatter")])
+def test_basis_checksums(m, n, order, name):
+    t, b = O.basis(m, n, order)
+    assert (checksum_basis(t, b) == G[f"basissum_{m}_{n}_{name}"]).all()
+
+
+def nbr_of(lat, m):
+    if lat == "chain":
+        return O.chain(m)
+    lx, ly = [int(v) for v in lat.split("-")[1:]]
+    return O.rect(lx, ly)
+
+
+@pytest.mark.parametrize("m,n,lat", [(3, 2, "chain"), (4, 4, "chain"), (5, 5, "chain"), (2, 5, "chain"), (6, 3, "rect-3-2"),
+                                     (4, 3, "rect-2-2")])
+def test_csc_bit_exact(m, n, lat):
+    t, b = O.basis(m, n)
+    nbr = nbr_of(lat, m)
+    jc = O.hopping_csc(m, nbr, t, b)
+    dU, dN = O.diagonals(m, b)
+    tag = f"{m}_{n}_{lat}"
+    for a, nm in zip(jc, ("outer", "inner", "val")):
+        assert (a == G[f"csc_J_{tag}_{nm}"]).all()
+    assert (dU == G[f"csc_U_{tag}_val"]).all() and (dN == G[f"csc_u_{tag}_val"]).all()
+    h = O.hsum_csc(jc, dU, dN, 1.0, 4.0, 1.0)
+    for a, nm in zip(h, ("outer", "inner", "val")):
+        assert (a == G[f"hsum_{tag}_{nm}"]).all()
+
+
+@pytest.mark.parametrize("m,n", [(8, 8)])
+def test_csc_checksum(m, n):
+    t, b = O.basis(m, n)
+    o, i, v = O.hopping_csc(m, O.chain(m), t, b)
+    assert (checksum_csc(o, i, v) == G[f"cscsum_J_{m}_{n}"]).all()
+
+
+@pytest.mark.parametrize("m,n", [(6, 6), (8, 8)])
+def test_spmv_and_lcg(m, n):
+    t, b = O.basis(m, n)
+    jc = O.hopping_csc(m, O.chain(m), t, b)
+    dU, dN = O.diagonals(m, b)
+    x = O.lcg_vector(len(t))
+    assert (bits(x) == bits(G[f"hv_{m}_{n}_x"])).all()          # Spectra's SimpleRandom sequence
+    y = O.spmv(O.hsum_csc(jc, dU, dN, 1.0, 4.0, 1.0), x)
+    want = G[f"hv_{m}_{n}_y"]
+    assert np.abs(y - want).max() <= 4e-15 * np.abs(want).max()  # the reference build may contract to FMA
+
+
+POINTS = [(5, 5, 1, 4, 1), (5, 5, 0.5, 1, 0), (6, 6, 1, 4, 1), (6, 6, 1, 0.5, 0), (7, 6, 1, 2, 3), (8, 8, 1, 4, 1), (8, 8, 1, 1, 0),
+          (8, 8, 1, 10, 0)]
+
+
+@pytest.mark.parametrize("m,n,cJ,cU,cu", POINTS)
+def test_point(m, n, cJ, cU, cu):
+    t, b = O.basis(m, n)
+    jc = O.hopping_csc(m, O.chain(m), t, b)
+    dU, dN = O.diagonals(m, b)
+    r = O.point(m, t, b, jc, dU, dN, float(cJ), float(cU), float(cu))
+    key = f"point_{m}_{n}_{cJ}_{cU}_{cu}"
+    want = G[key + "_evals"]
+    scale = np.maximum(np.abs(want), np.abs(want[0]))
+    assert np.all(np.abs(r["evals"] - want) <= 1e-10 * scale)
+    assert np.abs(r["rho"] - G[key + "_rho"]).max() <= 1e-10 * np.abs(G[key + "_rho"]).max()
+    assert np.allclose(r["out3"], G[key + "_out5"][2:], rtol=1e-9, atol=1e-12)
+
+
+def test_known_answers():
+    # KA3: U = 0 -> E0 = -4 J n and the next level E0 + 4J(1 - cos 2pi/m), twice
+    m = n = 6
+    t, b = O.basis(m, n)
+    jc = O.hopping_csc(m, O.chain(m), t, b)
+    dU, dN = O.diagonals(m, b)
+    e = O.eigs_sym(O.hsum_csc(jc, dU, dN, 1.0, 0.0, 0.0))["evals"]
+    assert abs(e[0] + 24.0) < 1e-10 and abs(e[1] - (-24 + 4 * (1 - np.cos(2 * np.pi / m)))) < 1e-10 and abs(e[2] - e[1]) < 1e-10
+    # KA4: J = 0 -> ground value 2 U n - mu n at m = n ; dense cross-check (Op::exact_eigen)
+    m = n = 4
+    t, b = O.basis(m, n)
+    dU, dN = O.diagonals(m, b)
+    assert min(3.0 * dU + 0.5 * dN) == 2 * 3.0 * n - 0.5 * n
+    jc = O.hopping_csc(m, O.chain(m), t, b)
+    o, i, v = O.hsum_csc(jc, dU, dN, 1.0, 2.0, 0.3)
+    dense = np.zeros((len(t), len(t)))
+    for c in range(len(t)):
+        dense[i[o[c]:o[c + 1]], c] = v[o[c]:o[c + 1]]
+    assert np.abs(dense - dense.T).max() == 0
+    ev = O.dense_sym_eig(dense)
+    assert np.abs(ev - np.linalg.eigvalsh(dense)).max() < 1e-11
+    # gap ratios / coherence on hand-made data
+    assert np.allclose(O.gap_ratios(np.array([0.0, 1.0, 3.0, 3.0, 4.0])), [0.5, 0.0, 0.0])

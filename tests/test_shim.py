@@ -1,0 +1,124 @@
+"""GPU: the C++ drop-in layer.  host/shim_test (BH::, Op::, Neighbours with Eigen types) takes the same commands
+as the reference harness; QuantumProject is the reference CLI on the B200 path and must reproduce the patched
+reference's phase.txt (tests/golden/phase_*.txt)."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "bose-hubbard-phase-transition_b200")
+SHIM = os.path.join(PKG, "shim_test")
+CLI = os.path.join(PKG, "QuantumProject")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def run_shim(args, names, expect_rc=0):
+    if not os.path.exists(SHIM):
+        pytest.skip("host/shim_test not built (needs Eigen headers at build time)")
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "o")
+        argv = [SHIM] + [str(a) if a != "@out" else out for a in args]
+        p = subprocess.run(argv, capture_output=True, text=True, timeout=600)
+        assert p.returncode == expect_rc, (p.returncode, p.stdout, p.stderr)
+        info = json.loads(p.stdout.strip().splitlines()[-1])
+        res = {}
+        for name, dt in names:
+            f = f"{out}.{name}.{'f64' if dt == np.float64 else 'i32'}"
+            if os.path.exists(f):
+                res[name] = np.fromfile(f, dtype=dt)
+        return info, res
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+@pytest.mark.parametrize("m,n", [(4, 4), (6, 6), (8, 8)])
+def test_fixed_set_basis(m, n):
+    for extra, order in (([], O.TAG_SORTED), (["scatter"], O.REF_SCATTER)):
+        _, r = run_shim(["basis", m, n, "@out"] + extra, [("tags", np.float64), ("basis", np.float64)])
+        t, b = O.basis(m, n, order)
+        assert (bits(r["tags"]) == bits(t)).all() and (r["basis"].reshape(-1, m) == b).all()
+
+
+@pytest.mark.parametrize("m,n,lat", [(5, 5, "chain"), (8, 8, "chain"), (6, 4, "rect:3:2"), (5, 4, "openchain")])
+def test_fixed_bosons_hamiltonian(m, n, lat):
+    nbr = O.chain(m) if lat == "chain" else O.chain(m, False) if lat == "openchain" else O.rect(3, 2)
+    t, b = O.basis(m, n)
+    jc = O.hopping_csc(m, nbr, t, b)
+    dU, dN = O.diagonals(m, b)
+    names = [("outer", np.int32), ("inner", np.int32), ("val", np.float64)]
+    _, r = run_shim(["csc", m, n, "J", lat, "@out"], names)
+    for a, nm in zip(jc, ("outer", "inner", "val")):
+        assert (r[nm] == a).all()
+    _, r = run_shim(["csc", m, n, "U", lat, "@out"], names)
+    assert (r["val"] == dU).all()
+    _, r = run_shim(["csc", m, n, "u", lat, "@out"], names)
+    assert (r["val"] == dN).all()
+
+
+@pytest.mark.parametrize("m,n,pars", [(6, 6, (1, 4, 1)), (8, 8, (1, 4, 1))])
+def test_irlm_eigen_on_eigen_sparse_matrix(m, n, pars):
+    info, r = run_shim(["eigs", m, n, *pars, 20, "chain", "@out"],
+                       [("evals", np.float64), ("H.outer", np.int32), ("H.inner", np.int32), ("H.val", np.float64)])
+    t, b = O.basis(m, n)
+    jc = O.hopping_csc(m, O.chain(m), t, b)
+    dU, dN = O.diagonals(m, b)
+    h = O.hsum_csc(jc, dU, dN, *[float(p) for p in pars])
+    for a, nm in zip(h, ("H.outer", "H.inner", "H.val")):   # the Eigen expression on shim matrices = reference H
+        assert (r[nm] == a).all()
+    want = O.eigs_sym(h)["evals"]
+    assert np.all(np.abs(r["evals"] - want) <= 1e-10 * np.maximum(np.abs(want), abs(want[0])))
+    assert info["max_residual"] <= 1e-9
+
+
+def test_irlm_eigen_error_like_spectra():
+    info, _ = run_shim(["eigs", 4, 4, 1, 4, 1, 20, "chain", "@out"], [], expect_rc=3)
+    assert info["exception"] == "invalid_argument" and "ncv must satisfy" in info["what"]
+
+
+def read_phase(text):
+    lines = [l for l in text.split("\n") if l]
+    return lines[0], np.array([[float(v) for v in l.split()] for l in lines[1:]])
+
+
+CLI_RUNS = {
+    "phase_m5_fJ.txt": ["-m", 5, "-n", 5, "-J", 1, "-U", 0, "-u", 0, "-r", 2, "-s", 1, "-f", "J", "-t", "exact"],
+    "phase_m5_fU.txt": ["-m", 5, "-n", 5, "-J", 0.5, "-U", 2, "-u", 1, "-r", 1, "-s", 0.5, "-f", "U", "-t", "exact"],
+    "phase_m5_fu.txt": ["-m", 5, "-n", 5, "-J", 0.5, "-U", 2, "-u", 1, "-r", 1, "-s", 0.5, "-f", "u", "-t", "exact"],
+    "phase_m6_fJ.txt": ["-m", 6, "-n", 6, "-J", 1, "-U", 0, "-u", 0, "-r", 3, "-s", 1, "-f", "J", "-t", "exact"],
+    "phase_m8_fJ.txt": ["-m", 8, "-n", 8, "-J", 1, "-U", 0, "-u", 0, "-r", 2, "-s", 1, "-f", "J", "-t", "exact"],
+}
+
+
+@pytest.mark.parametrize("name", sorted(CLI_RUNS))
+def test_cli_phase_txt(name):
+    with tempfile.TemporaryDirectory() as td:
+        p = subprocess.run([CLI] + [str(a) for a in CLI_RUNS[name]], cwd=td, capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, (p.stdout[-500:], p.stderr[-500:])
+        assert "Calculation duration:" in p.stdout and "Memory usage:" in p.stdout and "Progress: [" in p.stdout
+        got = open(os.path.join(td, "phase.txt")).read()
+    want = open(os.path.join(GOLD, name)).read()
+    h1, g = read_phase(got)
+    h2, w = read_phase(want)
+    assert h1 == h2 and g.shape == w.shape
+    assert np.array_equal(g[:, :2], w[:, :2])
+    assert np.allclose(g[:, 2:], w[:, 2:], rtol=2e-6, atol=1e-9)   # 6 significant digits in the file
+    same_text = sum(a == b for a, b in zip(got.split("\n"), want.split("\n")))
+    assert same_text >= len(want.split("\n")) - 1                  # text identical up to one last-digit rounding
+
+
+def test_cli_validation_messages():
+    p = subprocess.run([CLI, "-t", "foo"], capture_output=True, text=True)
+    assert p.returncode == 1 and "calculation type must be 'exact' or 'mean'" in p.stderr
+    p = subprocess.run([CLI, "-t", "exact", "-m", "5", "-n", "5", "-J", "1", "-r", "1", "-s", "2", "-f", "J"], capture_output=True, text=True)
+    assert p.returncode == 1 and "s must be smaller than r" in p.stderr
+    p = subprocess.run([CLI, "-t", "exact", "-m", "5", "-n", "5", "-J", "1", "-r", "2", "-s", "1", "-f", "x"], capture_output=True, text=True)
+    assert p.returncode == 1 and "fixed parameter must be J, U or u" in p.stderr

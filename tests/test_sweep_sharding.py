@@ -1,0 +1,83 @@
+"""CPU: host-side sweep logic -- range plumbing, grid arithmetic, phase.txt format, and the N > 1 sharding
+path over torch.distributed (gloo, world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def sweep_mod():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.load_package()
+    from bose_hubbard_phase_transition_b200 import sweep
+    return sweep
+
+
+def test_grid_matches_reference_plumbing():
+    sw = sweep_mod()
+    for name, args in [("phase_m5_fJ.txt", ("J", 1, 0, 0, 2, 1)), ("phase_m5_fU.txt", ("U", 0.5, 2, 1, 1, 0.5)),
+                       ("phase_m5_fu.txt", ("u", 0.5, 2, 1, 1, 0.5)), ("phase_m6_fJ.txt", ("J", 1, 0, 0, 3, 1))]:
+        lines = open(os.path.join(GOLD, name)).read().split("\n")
+        g = sw.make_grid(*args)
+        assert lines[0] == f"{g['fixed']} {sw.fmt(g['fixed_value'])}"
+        rows = [l.split() for l in lines[1:] if l]
+        assert len(rows) == g["num1"] * g["num2"]
+        table = {}
+        for (index, p1, p2, cJ, cU, cmu) in g["points"]:
+            table[index] = (p1, p2)
+        for k, row in enumerate(rows):
+            assert row[0] == sw.fmt(table[k][0]) and row[1] == sw.fmt(table[k][1])
+    # non-integer step: the count is int((max - min) / s) + 1 evaluated in double
+    g = sw.make_grid("J", 0.1, 0, 0, 1.0, 0.1)
+    assert g["num1"] == int((0.1 + 1.0 - 0.1) / 0.1) + 1
+
+
+def test_variance_rule_and_format():
+    sw = sweep_mod()
+    assert sw.needs_more_eigenvalues([0.2, 0.2, 0.2])
+    assert not sw.needs_more_eigenvalues([0.2, 0.25, 0.1])
+    assert sw.fmt(0.0750343123) == "0.0750343" and sw.fmt(1.0) == "1" and sw.fmt(1.5) == "1.5"
+
+
+def fake_point(cJ, cU, cmu, nb):
+    return (np.sin(cJ + 2 * cU) ** 2, 0.5 + 0.01 * cU, 0.25 * cJ + 0.125 * cmu)
+
+
+def worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sw = sweep_mod()
+    g = sw.make_grid("J", 1, 0, 0, 4, 1)
+    rows = sw.run_sweep(fake_point, g, world, rank, dist)
+    q.put((rank, rows))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sweep_equals_serial():
+    sw = sweep_mod()
+    g = sw.make_grid("J", 1, 0, 0, 4, 1)
+    serial = sw.run_sweep(fake_point, g)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert np.array_equal(got[0], serial) and np.array_equal(got[1], serial)
+    assert sorted(sw.shard(25, 2, 0) + sw.shard(25, 2, 1)) == list(range(25))
