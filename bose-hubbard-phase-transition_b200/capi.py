@@ -28,7 +28,7 @@ SYMBOLS = [
 
 
 class EigsInfo(C.Structure):
-    _fields_ = [("nconv", C.c_int32), ("nmatvec", C.c_int32), ("nrestart", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("nconv", C.c_int32), ("nmatvec", C.c_int32), ("nrestart", C.c_int32), ("nreorth", C.c_int32),
                 ("seconds", C.c_double)]
 
 
@@ -264,7 +264,7 @@ class Context:
         if rc and not (allow_noconv and rc == ERR_NOCONV):
             self._check(rc)
         return dict(evals=ev, vecs=vecs, nconv=info.nconv, nmatvec=info.nmatvec, nrestart=info.nrestart,
-                    seconds=info.seconds, rc=rc)
+                    nreorth=info.nreorth, seconds=info.seconds, rc=rc)
 
     def spdm(self, phi, ncols=20, order=TAG_SORTED):
         phi = np.ascontiguousarray(phi, dtype=np.float64)
@@ -280,7 +280,7 @@ class Context:
         self._check(self.L.bh_point(self.h, cJ, cU, cmu, nb_eigen, kernel, _ptr(out3), _ptr(ev), _ptr(rho),
                                     C.byref(info)))
         return dict(out3=out3, evals=ev, rho=rho.T.copy(), nmatvec=info.nmatvec, nrestart=info.nrestart,
-                    seconds=info.seconds)
+                    nreorth=info.nreorth, seconds=info.seconds)
 
     def points(self, cJ, cU, cmu, nb_eigen=20, kernel=HV_STORED):
         cJ = np.ascontiguousarray(cJ, dtype=np.float64)

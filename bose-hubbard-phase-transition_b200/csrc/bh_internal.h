@@ -78,6 +78,8 @@ struct bh_ctx {
     int* d_perm_tag = nullptr;
     int* d_inv_tag = nullptr;
 
+    int reorth_block = 8;  // basis columns per re-orthogonalisation block (env BH_REORTH_BLOCK)
+    bool reorth_block_forced = false;
     // Lanczos workspace (lazy)
     int ws_ncv = 0;
     double* d_V = nullptr;      // (ws_ncv + 1) columns of ld doubles

@@ -59,6 +59,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     }
     ctx->own_stream = true;
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
+    if (const char* v = getenv("BH_REORTH_BLOCK")) { ctx->reorth_block = std::min(BH_MAX_NCV, std::max(1, atoi(v))); ctx->reorth_block_forced = true; }
     if (const char* v = getenv("BH_HV_STAGES")) ctx->hv_stages = std::min(4, std::max(2, atoi(v)));
     *out = ctx;
     return BH_OK;

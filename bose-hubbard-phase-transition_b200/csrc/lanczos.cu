@@ -130,36 +130,40 @@ k_resid_norm(int64_t D, const double* __restrict__ w, const double* __restrict__
     }
 }
 
-// vf[0..cnt) = V[:, 0..cnt)^T f ; then alpha_i += vf[i], offd_i += vf[i-1]   (Lanczos.h:150-158,166-171)
+
+// ---- full re-orthogonalisation of the residual, in column blocks of at most GT_CH basis vectors ----------
+// For each block B of columns (block modified Gram-Schmidt): k_gemv_t computes c_B = V_B^T f, k_gemv_n_norm
+// applies f -= V_B c_B.  A block is small enough (GT_CH * 8 * D bytes) to stay in L2 between the two kernels, so
+// the basis is read from HBM once per Lanczos step rather than twice.  Rows are handled in pairs (16-byte loads).
+//
+// c[col0 .. col0+cnt) = V[:, col0 .. col0+cnt)^T f ; then alpha_i += c[i], offd_i += c[i-1]  (Lanczos.h:150-171)
+// (cnt may exceed GT_CH: the columns are then swept in chunks of GT_CH with f re-read from L1/L2 -- used for
+//  small systems whose whole basis is L2-resident, where fewer launches matter more than HBM passes)
+template <bool MULTI>
 __global__ void __launch_bounds__(VEC_THREADS)
-k_gemv_t(int64_t D, int64_t ld, const double* __restrict__ V, int cnt, const double* __restrict__ f,
+k_gemv_t(int64_t D, int64_t ld, const double* __restrict__ V, int col0, int cnt, const double* __restrict__ f,
          double* __restrict__ scal, int i, int fix_offd, double* __restrict__ part, unsigned int* __restrict__ counter)
 {
     __shared__ double red[VEC_THREADS / 32][GT_CH];
-    // contiguous row range per block so that f stays in L1/L2 across the column sweeps
-    const int64_t per = ((D + gridDim.x - 1) / gridDim.x + 3) & ~(int64_t)3;
-    const int64_t r0 = (int64_t)blockIdx.x * per;
-    const int64_t r1 = min(r0 + per, D);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int c0 = 0; c0 < cnt; c0 += GT_CH) {
+    const int64_t npair = (D + 1) >> 1;  // ld is even and the padding is zero
+    const double2* f2 = reinterpret_cast<const double2*>(f);
+    const int64_t ld2 = ld >> 1;
+    const int pstride = MULTI ? NC : GT_CH;
+    const int ncc = MULTI ? cnt : 1;  // single-chunk instantiation: cnt <= GT_CH, loop body runs once
+    for (int cc = 0; cc < ncc; cc += GT_CH) {
+        const int nc = min(GT_CH, cnt - cc);
+        const double2* V2 = reinterpret_cast<const double2*>(V + (int64_t)(col0 + cc) * ld);
         double acc[GT_CH];
 #pragma unroll
         for (int j = 0; j < GT_CH; ++j) acc[j] = 0.0;
-        const int nc = min(GT_CH, cnt - c0);
-        const double* Vc = V + (int64_t)c0 * ld;
-        if (nc == GT_CH) {
-            for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-                const double fr = f[r];
+        for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < npair; r += (int64_t)gridDim.x * blockDim.x) {
+            const double2 fr = f2[r];
+            double2 v[GT_CH];
 #pragma unroll
-                for (int j = 0; j < GT_CH; ++j) acc[j] += Vc[(int64_t)j * ld + r] * fr;
-            }
-        } else {
-            for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-                const double fr = f[r];
+            for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? V2[(int64_t)j * ld2 + r] : make_double2(0.0, 0.0);
 #pragma unroll
-                for (int j = 0; j < GT_CH; ++j)
-                    if (j < nc) acc[j] += Vc[(int64_t)j * ld + r] * fr;
-            }
+            for (int j = 0; j < GT_CH; ++j) acc[j] = fma(v[j].x, fr.x, fma(v[j].y, fr.y, acc[j]));
         }
 #pragma unroll
         for (int j = 0; j < GT_CH; ++j) acc[j] = bh_warp_sum(acc[j]);
@@ -169,47 +173,66 @@ k_gemv_t(int64_t D, int64_t ld, const double* __restrict__ V, int cnt, const dou
             for (int j = 0; j < GT_CH; ++j) red[wid][j] = acc[j];
         }
         __syncthreads();
-        if (threadIdx.x < nc) {
+        if (threadIdx.x < GT_CH) {
             double t = 0.0;
             for (int w = 0; w < VEC_THREADS / 32; ++w) t += red[w][threadIdx.x];
-            part[(int64_t)blockIdx.x * NC + c0 + threadIdx.x] = t;
+            part[(int64_t)blockIdx.x * pstride + cc + threadIdx.x] = t;
         }
     }
     if (bh_last_block(counter)) {
-        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+        // one warp per column: lanes stride over the blocks' partial sums, fixed-order tree
+        for (int j = wid; j < cnt; j += VEC_THREADS / 32) {
             double t = 0.0;
-            for (int b = 0; b < (int)gridDim.x; ++b) t += part[(int64_t)b * NC + j];
-            scal[S_VF + j] = t;
-            if (j == i) scal[S_ALPHA + i] += t;
-            if (fix_offd && j == i - 1) scal[S_OFFD + i] += t;
+            for (int b = lane; b < (int)gridDim.x; b += 32) t += part[(int64_t)b * pstride + j];
+            t = bh_warp_sum(t);
+            if (lane == 0) {
+                const int c = col0 + j;
+                scal[S_VF + c] = t;
+                if (c == i) scal[S_ALPHA + i] += t;
+                if (fix_offd && c == i - 1) scal[S_OFFD + i] += t;
+            }
         }
     }
 }
 
-// f -= V[:, 0..cnt) vf ; beta_i = |f|
+// f -= V[:, col0 .. col0+cnt) c ; beta_i = |f|
+template <bool MULTI>
 __global__ void __launch_bounds__(VEC_THREADS)
-k_gemv_n_norm(int64_t D, int64_t ld, const double* __restrict__ V, int cnt, double* __restrict__ f,
+k_gemv_n_norm(int64_t D, int64_t ld, const double* __restrict__ V, int col0, int cnt, double* __restrict__ f,
               double* __restrict__ scal, int i, double* __restrict__ part, unsigned int* __restrict__ counter)
 {
-    __shared__ double coef[NC];
     __shared__ double scratch[32];
-    for (int j = threadIdx.x; j < cnt; j += blockDim.x) coef[j] = scal[S_VF + j];
-    __syncthreads();
+    __shared__ double coef[MULTI ? NC : GT_CH];
+    double creg[GT_CH];
+    if (MULTI) {
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) coef[j] = scal[S_VF + col0 + j];
+        __syncthreads();
+    } else {
+#pragma unroll
+        for (int j = 0; j < GT_CH; ++j) creg[j] = (j < cnt) ? scal[S_VF + col0 + j] : 0.0;
+    }
+    const int ncc = MULTI ? cnt : 1;
+    const int64_t npair = (D + 1) >> 1;
+    double2* f2 = reinterpret_cast<double2*>(f);
+    const int64_t ld2 = ld >> 1;
     double acc = 0.0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < D; r += (int64_t)gridDim.x * blockDim.x) {
-        double fr = f[r];
-        int j = 0;
-        for (; j + 4 <= cnt; j += 4) {
-            const double v0 = V[(int64_t)j * ld + r], v1 = V[(int64_t)(j + 1) * ld + r];
-            const double v2 = V[(int64_t)(j + 2) * ld + r], v3 = V[(int64_t)(j + 3) * ld + r];
-            fr -= v0 * coef[j];
-            fr -= v1 * coef[j + 1];
-            fr -= v2 * coef[j + 2];
-            fr -= v3 * coef[j + 3];
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < npair; r += (int64_t)gridDim.x * blockDim.x) {
+        double2 fr = f2[r];
+        for (int cc = 0; cc < ncc; cc += GT_CH) {
+            const int nc = min(GT_CH, cnt - cc);
+            const double2* V2 = reinterpret_cast<const double2*>(V + (int64_t)(col0 + cc) * ld);
+            double2 v[GT_CH];
+#pragma unroll
+            for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? V2[(int64_t)j * ld2 + r] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < GT_CH; ++j) {
+                const double c = MULTI ? ((j < nc) ? coef[cc + j] : 0.0) : creg[j];
+                fr.x = fma(-v[j].x, c, fr.x);
+                fr.y = fma(-v[j].y, c, fr.y);
+            }
         }
-        for (; j < cnt; ++j) fr -= V[(int64_t)j * ld + r] * coef[j];
-        f[r] = fr;
-        acc += fr * fr;
+        f2[r] = fr;
+        acc = fma(fr.x, fr.x, fma(fr.y, fr.y, acc));
     }
     acc = bh_block_sum(acc, scratch);
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
@@ -219,6 +242,15 @@ k_gemv_n_norm(int64_t D, int64_t ld, const double* __restrict__ V, int cnt, doub
         t = bh_block_sum(t, scratch);
         if (threadIdx.x == 0) scal[S_BETA + i + 1] = sqrt(t);
     }
+}
+
+// x *= 1 / scal[idx]  (final normalisation of a Ritz vector: under partial re-orthogonalisation the basis is
+// orthonormal only to sqrt(eps), so |V y| differs from 1 at that level)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_scale_inplace(int64_t D, double* __restrict__ x, const double* __restrict__ scal, int idx)
+{
+    const double inv = 1.0 / scal[idx];
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < D; r += (int64_t)gridDim.x * blockDim.x) x[r] *= inv;
 }
 
 // out = V[:, 0..cnt) y   (Ritz vector, HermEigsBase.h:456-479)
@@ -269,8 +301,15 @@ k_compress(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, const 
 int bh_ensure_workspace(bh_ctx* ctx, int ncv)
 {
     if (!ctx->D) return bh_fail(ctx, BH_ERR_STATE, "no system: call bh_setup first");
-    if (!ctx->d_w) BH_CUDA(ctx, cudaMalloc(&ctx->d_w, sizeof(double) * ctx->ld));
-    if (!ctx->d_f) BH_CUDA(ctx, cudaMalloc(&ctx->d_f, sizeof(double) * ctx->ld));
+    // vectors are padded to ld (a multiple of 32) with zeros: the re-orthogonalisation kernels read row pairs
+    if (!ctx->d_w) {
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_w, sizeof(double) * ctx->ld));
+        BH_CUDA(ctx, cudaMemsetAsync(ctx->d_w, 0, sizeof(double) * ctx->ld, ctx->stream));
+    }
+    if (!ctx->d_f) {
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_f, sizeof(double) * ctx->ld));
+        BH_CUDA(ctx, cudaMemsetAsync(ctx->d_f, 0, sizeof(double) * ctx->ld, ctx->stream));
+    }
     if (!ctx->d_scal) {
         BH_CUDA(ctx, cudaMalloc(&ctx->d_scal, sizeof(double) * S_TOTAL));
         BH_CUDA(ctx, cudaMalloc(&ctx->d_part, sizeof(double) * (size_t)NC * (ctx->sm_count * 8)));
@@ -282,6 +321,7 @@ int bh_ensure_workspace(bh_ctx* ctx, int ncv)
         if (ctx->d_V) cudaFree(ctx->d_V);
         ctx->d_V = nullptr;
         BH_CUDA(ctx, cudaMalloc(&ctx->d_V, sizeof(double) * (size_t)ctx->ld * (ncv + 1)));
+        BH_CUDA(ctx, cudaMemsetAsync(ctx->d_V, 0, sizeof(double) * (size_t)ctx->ld * (ncv + 1), ctx->stream));
         ctx->ws_ncv = ncv;
     }
     return BH_OK;
@@ -321,6 +361,9 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
     int from = 0, nconv = 0, iter = 0;
     double beta_last = 0.0;
     const int CRsel = (ncv <= 160) ? 64 : 16;
+    // column block of the re-orthogonalisation: L2-sized blocks for big systems, everything at once when the
+    // whole basis is L2-resident anyway (then launch count is what matters)
+    const int rblock = ((size_t)ld * 8 * (ncv + 1) <= ((size_t)48 << 20) && !ctx->reorth_block_forced) ? ncv + 1 : ctx->reorth_block;
     const size_t compress_smem = sizeof(double) * ((size_t)ncv * CRsel + (size_t)CK * ncv);
     if (compress_smem > 48 * 1024) {
         if (CRsel == 64)
@@ -340,11 +383,21 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
             k_local_alpha<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_w, i > 0 ? vi - ld : vi, vi, scal, i, subtract, part, counter);
             k_resid_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_w, vi, ctx->d_f, scal, i, part, counter);
             const int passes = first_after_restart ? 2 : 1;
+            int nlaunch = 3;
             for (int p = 0; p < passes; ++p) {
-                k_gemv_t<<<G, VEC_THREADS, 0, st>>>(D, ld, V, i + 1, ctx->d_f, scal, i, subtract, part, counter);
-                k_gemv_n_norm<<<G, VEC_THREADS, 0, st>>>(D, ld, V, i + 1, ctx->d_f, scal, i, part, counter);
+                for (int c0 = 0; c0 <= i; c0 += rblock) {
+                    const int cnt = std::min(rblock, i + 1 - c0);
+                    if (rblock <= GT_CH) {
+                        k_gemv_t<false><<<G, VEC_THREADS, 0, st>>>(D, ld, V, c0, cnt, ctx->d_f, scal, i, subtract, part, counter);
+                        k_gemv_n_norm<false><<<G, VEC_THREADS, 0, st>>>(D, ld, V, c0, cnt, ctx->d_f, scal, i, part, counter);
+                    } else {
+                        k_gemv_t<true><<<G, VEC_THREADS, 0, st>>>(D, ld, V, c0, cnt, ctx->d_f, scal, i, subtract, part, counter);
+                        k_gemv_n_norm<true><<<G, VEC_THREADS, 0, st>>>(D, ld, V, c0, cnt, ctx->d_f, scal, i, part, counter);
+                    }
+                    nlaunch += 2;
+                }
             }
-            ctx->launches += 3 + 2 * passes;
+            ctx->launches += nlaunch;
         }
         BH_CUDA(ctx, cudaGetLastError());
         BH_D2H(ctx, h_scal.data(), scal, sizeof(double) * S_TOTAL);
@@ -402,6 +455,7 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
     out->info.nconv = std::min(nconv, nev);
     out->info.nmatvec = nmatvec;
     out->info.nrestart = iter + 1;
+    out->info.nreorth = nmatvec - 1;  // every step re-orthogonalises (see DESIGN.md on partial re-orthogonalisation)
     out->info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     if (nconv < nev) return bh_fail(ctx, BH_ERR_NOCONV, "Eigenvalue computation failed.");
     return BH_OK;
@@ -412,7 +466,9 @@ int bh_ritz_vector(bh_ctx* ctx, const BhSolve& s, int col, double* x_dev)
     BH_H2D(ctx, ctx->d_small, s.Y.data() + (size_t)col * s.ncv, sizeof(double) * s.ncv);
     const int G = (int)std::min<int64_t>(nblocks(ctx->D, VEC_THREADS), (int64_t)ctx->sm_count * 4);
     k_lincomb<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->D, ctx->ld, ctx->d_V, s.ncv, ctx->d_small, x_dev);
-    BH_LAUNCHED(ctx);
+    k_norm<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->D, x_dev, ctx->d_scal, S_VF, ctx->d_part, ctx->d_counter);
+    k_scale_inplace<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->D, x_dev, ctx->d_scal, S_VF);
+    ctx->launches += 3;
     BH_CUDA(ctx, cudaGetLastError());
     return BH_OK;
 }

@@ -93,7 +93,7 @@ typedef struct bh_eigs_info {
     int32_t nconv;     /* converged wanted pairs */
     int32_t nmatvec;   /* H.v applications */
     int32_t nrestart;  /* restarts (Spectra's num_iterations) */
-    int32_t reserved;
+    int32_t nreorth;   /* Lanczos steps that ran the full re-orthogonalisation pass */
     double seconds;    /* device+host wall time of the solve */
 } bh_eigs_info;
 /* nev smallest eigenvalues (ascending) of H(cJ,cU,cmu); thick-restart Lanczos with Spectra's

@@ -15,7 +15,7 @@ if not use_ref:
 for U in Us:
     for kern in (0, 1):
         r = ctx.eigs(1.0, U, 1.0, kernel=kern, allow_noconv=True)
-        print(f"m={m} U={U} kernel={kern}: gpu nmatvec={r['nmatvec']} nrestart={r['nrestart']} nconv={r['nconv']} t={r['seconds']*1e3:.1f} ms E0={r['evals'][0]:.12f}", flush=True)
+        print(f"m={m} U={U} kernel={kern}: gpu nmatvec={r['nmatvec']} nrestart={r['nrestart']} nreorth={r['nreorth']} nconv={r['nconv']} t={r['seconds']*1e3:.1f} ms E0={r['evals'][0]:.12f}", flush=True)
     if use_ref:
         rr, info = R.eigs(m, n, 1, U, 1)
         print(f"     ref nmatvec={info['nmatvec']} nrestart={info['nrestart']} t={info['seconds']:.2f}s maxdiff={np.abs(np.sort(rr['evals'])-r['evals']).max():.2e}", flush=True)
