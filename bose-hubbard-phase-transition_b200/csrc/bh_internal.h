@@ -22,7 +22,10 @@ struct BhTables {
     // w[dst][src]: how many times the ordered bond appears in the neighbour list, both directions summed
     // (the reference pushes (index,k) and (k,index) for every listed neighbour, src/hamiltonian.cpp:184-185).
     unsigned char w[BH_MAX_SITES][BH_MAX_SITES];
+    int chain;   // 1 = open chain, 2 = closed chain (every nearest-neighbour bond listed from both ends, w = 2), else 0
     int nbonds;  // ordered pairs with w > 0
+    // the same pairs as a list, ordered by (src, dst): dst | src << 4 | w << 8
+    unsigned short bond[BH_MAX_SITES * (BH_MAX_SITES - 1)];
     // sq[a] = sqrt(a) for the amplitudes sqrt((n_dst + 1) * n_src), a <= 16 * 15
     double sq[256];
     double logp[BH_MAX_SITES];  // log(prime_i), host glibc values (src/hamiltonian.cpp:94,144)
@@ -46,6 +49,7 @@ struct bh_ctx {
     BhTables h_tab;
     BhTables* d_tab = nullptr;
     int max_row = 0;  // max entries per row of H (incl. diagonal)
+    int free_variant = 1;  // matrix-free H.v: 0 = fully unrolled site pairs, 1 = bond list + shared-memory prefixes (env BH_FREE_VARIANT)
     int hv_variant = 2;  // stored H.v: 0 = CSR-stream, 1 = TMA-staged CSR-stream, 2 = SELL-32 (default; env BH_HV_VARIANT)
     int hv_stages = 3;   // ring depth of the TMA variant (env BH_HV_STAGES)
     int tile_cap = 0;    // entries per shared-memory stage of the TMA variant

@@ -59,6 +59,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     }
     ctx->own_stream = true;
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
+    if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
     if (const char* v = getenv("BH_REORTH_BLOCK")) { ctx->reorth_block = std::min(BH_MAX_NCV, std::max(1, atoi(v))); ctx->reorth_block_forced = true; }
     if (const char* v = getenv("BH_HV_STAGES")) ctx->hv_stages = std::min(4, std::max(2, atoi(v)));
     *out = ctx;
@@ -294,9 +295,23 @@ int bh_build_basis(bh_ctx* ctx)
             t.w[i][src]++;
             t.w[src][i]++;
         }
-    for (int i = 0; i < m; ++i)
-        for (int j = 0; j < m; ++j) nb += t.w[i][j] > 0;
+    for (int src = 0; src < m; ++src)
+        for (int dst = 0; dst < m; ++dst)
+            if (t.w[dst][src] > 0) t.bond[nb++] = (unsigned short)(dst | (src << 4) | (t.w[dst][src] << 8));
     t.nbonds = nb;
+    // recognise the reference's chains (src/neighbours.cpp:21-34): the chain-specialised H.v kernel needs no prefix arrays
+    t.chain = 0;
+    if (m >= 3) {
+        bool open_ok = true, closed_ok = true;
+        for (int a = 0; a < m; ++a)
+            for (int b2 = 0; b2 < m; ++b2) {
+                const bool nn = (a - b2 == 1 || b2 - a == 1);
+                const bool wrap = (a == 0 && b2 == m - 1) || (a == m - 1 && b2 == 0);
+                if (t.w[a][b2] != (nn ? 2 : 0)) open_ok = false;
+                if (t.w[a][b2] != ((nn || wrap) ? 2 : 0)) closed_ok = false;
+            }
+        t.chain = closed_ok ? 2 : (open_ok ? 1 : 0);
+    }
     ctx->max_row = nb + 1;
 
     BH_CUDA(ctx, cudaMalloc(&ctx->d_tab, sizeof(BhTables)));

@@ -266,6 +266,121 @@ k_hv_free(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restri
     }
 }
 
+typedef void (*hv_free_fn_t)(const BhTables*, int64_t, const uint64_t*, const double*, double, double, double,
+                             const double*, double*);
+
+// K4, bond-list variant: the per-thread rank prefixes live in shared memory ([site][thread], conflict-free),
+// so the hop loop runs over the lattice's actual bond list (uniform across the block) instead of all site
+// pairs, and one kernel serves every m.  ~4x fewer instructions per row than the unrolled variant.
+#define HVF_THREADS 256
+__global__ void __launch_bounds__(HVF_THREADS)
+k_hv_free_bonds(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restrict__ states,
+                const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
+                double* __restrict__ y)
+{
+    __shared__ BhTables t;
+    __shared__ int sdn[BH_MAX_SITES][HVF_THREADS];
+    __shared__ int sup[BH_MAX_SITES][HVF_THREADS];
+    bh_stage_tables(&t, gtab);
+    const int tid = threadIdx.x;
+    const int m = t.m, nb = t.nbonds;
+    const double shift = __dmul_rn(-(double)t.n, cmu);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + tid; k < D; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = states[k];
+        int R = t.n, adn = 0, aup = 0;
+        for (int q = 0; q < m; ++q) {
+            sdn[q][tid] = adn;
+            sup[q][tid] = aup;
+            R -= bh_occ(s, q);
+            if (q < m - 1) {
+                const int f0 = t.f[q][R];
+                adn += (R >= 1 ? t.f[q][R - 1] : f0) - f0;
+                aup += t.f[q][R + 1] - f0;
+            }
+        }
+        double acc = 0.0;
+#pragma unroll 4
+        for (int b = 0; b < nb; ++b) {
+            const int bd = t.bond[b];
+            const int dst = bd & 15, src = (bd >> 4) & 15, w = bd >> 8;
+            const int ns = bh_occ(s, src);
+            const int delta = (dst < src) ? sdn[src][tid] - sdn[dst][tid] : sup[dst][tid] - sup[src][tid];
+            const double xv = ns ? __ldg(x + (int)k + delta) : 0.0;
+            acc = fma((double)w * t.sq[(bh_occ(s, dst) + 1) * ns], xv, acc);
+        }
+        const double diag = __dadd_rn(__dmul_rn(dU[k], cU), shift);
+        y[k] = diag * x[k] - cJ * acc;
+    }
+}
+
+// K4, chain-specialised variant (the reference CLI only ever builds the closed chain, src/analysis.cpp:219-220):
+// a nearest-neighbour hop across bond (q, q+1) changes the rank by ONE table difference that depends on
+// (q, R_q) only, so the row is produced in a single sweep over the sites with no prefix arrays; the periodic
+// bond uses the accumulated totals.  ~3x fewer instructions per row than the bond-list kernel.
+template <int M, bool CLOSED>
+__global__ void __launch_bounds__(256)
+k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restrict__ states,
+                const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
+                double* __restrict__ y)
+{
+    __shared__ BhTables t;
+    bh_stage_tables(&t, gtab);
+    const double shift = __dmul_rn(-(double)t.n, cmu);
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < D; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = states[k];
+        const double* xk = x + k;
+        const int n0 = bh_occ(s, 0);
+        int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < M - 1; ++q) {
+            const int nnext = bh_occ(s, q + 1);
+            const int f0 = t.f[q][R];
+            const int g = (R >= 1 ? t.f[q][R - 1] : f0) - f0;  // boson moves q+1 -> q
+            const int h = t.f[q][R + 1] - f0;                   // boson moves q -> q+1
+            const double xa = nnext ? __ldg(xk + g) : 0.0;
+            const double xb = nprev ? __ldg(xk + h) : 0.0;
+            acc = fma(t.sq[(nprev + 1) * nnext], xa, acc);
+            acc = fma(t.sq[(nnext + 1) * nprev], xb, acc);
+            tdn += g;
+            tup += h;
+            R -= nnext;
+            nprev = nnext;
+        }
+        if (CLOSED) {
+            const int nl = nprev;  // occupation of the last site
+            const double xa = nl ? __ldg(xk + tdn) : 0.0;  // M-1 -> 0
+            const double xb = n0 ? __ldg(xk + tup) : 0.0;  // 0 -> M-1
+            acc = fma(t.sq[(n0 + 1) * nl], xa, acc);
+            acc = fma(t.sq[(nl + 1) * n0], xb, acc);
+        }
+        const double diag = __dadd_rn(__dmul_rn(dU[k], cU), shift);
+        y[k] = diag * x[k] - (2.0 * cJ) * acc;
+    }
+}
+
+template <bool CLOSED>
+static hv_free_fn_t hv_chain_kernel(int m)
+{
+    switch (m) {
+        case 3: return k_hv_free_chain<3, CLOSED>;
+        case 4: return k_hv_free_chain<4, CLOSED>;
+        case 5: return k_hv_free_chain<5, CLOSED>;
+        case 6: return k_hv_free_chain<6, CLOSED>;
+        case 7: return k_hv_free_chain<7, CLOSED>;
+        case 8: return k_hv_free_chain<8, CLOSED>;
+        case 9: return k_hv_free_chain<9, CLOSED>;
+        case 10: return k_hv_free_chain<10, CLOSED>;
+        case 11: return k_hv_free_chain<11, CLOSED>;
+        case 12: return k_hv_free_chain<12, CLOSED>;
+        case 13: return k_hv_free_chain<13, CLOSED>;
+        case 14: return k_hv_free_chain<14, CLOSED>;
+        case 15: return k_hv_free_chain<15, CLOSED>;
+        case 16: return k_hv_free_chain<16, CLOSED>;
+    }
+    return nullptr;
+}
+
 typedef void (*hv_free_fn)(const BhTables*, int64_t, const uint64_t*, const double*, double, double, double,
                            const double*, double*);
 
@@ -346,9 +461,18 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, cons
             BH_LAUNCHED(ctx);
         }
     } else if (kernel == BH_HV_MATRIX_FREE) {
-        hv_free_fn fn = hv_free_kernel(ctx->m);
-        int grid = (int)std::min<int64_t>(nblocks(D, 256), (int64_t)ctx->sm_count * 8);
-        fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x, y);
+        if (ctx->free_variant == 1 && ctx->h_tab.chain) {
+            hv_free_fn_t fn = (ctx->h_tab.chain == 2) ? hv_chain_kernel<true>(ctx->m) : hv_chain_kernel<false>(ctx->m);
+            int grid = (int)std::min<int64_t>(nblocks(D, 256), (int64_t)ctx->sm_count * 8);
+            fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x, y);
+        } else if (ctx->free_variant >= 1) {
+            int grid = (int)std::min<int64_t>(nblocks(D, HVF_THREADS), (int64_t)ctx->sm_count * 5);
+            k_hv_free_bonds<<<grid, HVF_THREADS, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x, y);
+        } else {
+            hv_free_fn fn = hv_free_kernel(ctx->m);
+            int grid = (int)std::min<int64_t>(nblocks(D, 256), (int64_t)ctx->sm_count * 8);
+            fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x, y);
+        }
         BH_LAUNCHED(ctx);
     } else {
         return bh_fail(ctx, BH_ERR_ARG, "unknown H.v kernel");
