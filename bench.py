@@ -283,10 +283,10 @@ def main():
     tf = os.path.join(ROOT, "profiles", "hv_traffic.json")
     if os.path.exists(tf):
         try:
-            traffic = json.load(open(tf)).get("k_hv_csr_dram_bytes_per_launch")
+            traffic = json.load(open(tf)).get("k_hv_sell_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_hv_csr (stored-CSR H.v, K3)", "achieved": hv["stored"]["gbs"], "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_hv_sell (stored H.v, K3, SELL-32 layout)", "achieved": hv["stored"]["gbs"], "peak": peak,
                 "unit": "GB/s", "frac": hv["stored"]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": hv["stored"]["algorithmic_bytes"], "ms_per_launch": hv["stored"]["ms"]}
 
