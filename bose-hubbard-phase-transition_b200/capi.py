@@ -24,6 +24,7 @@ SYMBOLS = [
     "bh_term_nnz", "bh_term_csc", "bh_hamiltonian_nnz", "bh_hamiltonian_csc", "bh_hv", "bh_hv_dev", "bh_eigs",
     "bh_spdm", "bh_gap_ratios", "bh_condensate_fraction", "bh_coherence", "bh_point", "bh_points",
     "bh_lcg_fill_dev", "bh_hv_algorithmic_bytes", "bh_load_matrix",
+    "bh_dist_unique_id", "bh_dist_init", "bh_dist_finalize", "bh_setup_partitioned", "bh_partition",
 ]
 
 
@@ -81,6 +82,11 @@ def load():
     L.bh_coherence.argtypes = [C.c_int, vp, dp]
     L.bh_point.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, C.POINTER(EigsInfo)]
     L.bh_points.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
+    L.bh_dist_unique_id.argtypes = [vp]
+    L.bh_dist_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.bh_dist_finalize.argtypes = [vp]
+    L.bh_setup_partitioned.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.bh_partition.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.bh_load_matrix.argtypes = [vp, C.c_int64, vp, vp, vp]
     L.bh_lcg_fill_dev.argtypes = [vp, vp, C.c_int64]
     L.bh_hv_algorithmic_bytes.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
@@ -188,6 +194,35 @@ class Context:
         self.m, self.n, self.D = m, n, dimension(m, n)
         return self
 
+    # ---- row-partitioned solve over several GPUs (one process per GPU) ----
+    @staticmethod
+    def dist_unique_id():
+        buf = (C.c_ubyte * 128)()
+        rc = load().bh_dist_unique_id(buf)
+        if rc:
+            raise BhError(rc, load().bh_last_error(None).decode())
+        return bytes(buf)
+
+    def dist_init(self, world, rank, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self.L.bh_dist_init(self.h, world, rank, buf))
+
+    def dist_finalize(self):
+        self._check(self.L.bh_dist_finalize(self.h))
+
+    def setup_partitioned(self, m, n, nbr=None):
+        ptr, idx = nbr if nbr is not None else neighbours_chain(m)
+        ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        self._check(self.L.bh_setup_partitioned(self.h, m, n, _ptr(ptr), _ptr(idx)))
+        self.m, self.n, self.D = m, n, dimension(m, n)
+        return self
+
+    def partition(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self.L.bh_partition(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def load_matrix(self, outer, inner, val):
         outer = np.ascontiguousarray(outer, dtype=np.int32)
         inner = np.ascontiguousarray(inner, dtype=np.int32)
@@ -257,7 +292,8 @@ class Context:
              want_vectors=False, allow_noconv=False):
         ncv = ncv or 2 * nev + 1
         ev = np.full(nev, np.nan)
-        vecs = np.empty((nev, self.D)) if want_vectors else None
+        nrows = self.partition()[1] if want_vectors else 0
+        vecs = np.empty((nev, nrows)) if want_vectors else None
         info = EigsInfo()
         rc = self.L.bh_eigs(self.h, cJ, cU, cmu, nev, ncv, tol, maxit, kernel, order, _ptr(ev), _ptr(vecs),
                             C.byref(info))

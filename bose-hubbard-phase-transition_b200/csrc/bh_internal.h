@@ -44,7 +44,13 @@ struct bh_ctx {
     bool user_matrix = false;  // true after bh_load_matrix: no Fock basis, only the SELL copy of the given matrix
     int m = 0, n = 0;
     int64_t D = 0;
-    int64_t ld = 0;  // padded vector length (multiple of 32 doubles)
+    int64_t ld = 0;  // padded (local) vector length (multiple of 32 doubles)
+    // row partition (one large eigensolve over several GPUs): this context owns LEX ranks [row0, row0 + nloc)
+    int world = 1, rank = 0;
+    void* nccl_comm = nullptr;
+    bool partitioned = false;
+    int64_t row0 = 0, nloc = 0;
+    double* d_xfull = nullptr;  // all-gathered vector, world * ld doubles (global index = LEX rank)
     std::vector<int> nbr_ptr, nbr_idx;
     BhTables h_tab;
     BhTables* d_tab = nullptr;
@@ -82,6 +88,7 @@ struct bh_ctx {
     int* d_perm_tag = nullptr;
     int* d_inv_tag = nullptr;
 
+    int coop = 1;          // single cooperative launch per Lanczos step when the residual fits in registers (env BH_COOP)
     int reorth_block = 8;  // basis columns per re-orthogonalisation block (env BH_REORTH_BLOCK)
     bool reorth_block_forced = false;
     // Lanczos workspace (lazy)
@@ -150,6 +157,9 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
 // x_dev = V * Y[:, col]  (Ritz vector in LEX order)
 int bh_ritz_vector(bh_ctx* ctx, const BhSolve& s, int col, double* x_dev);
 int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host);
+// NCCL plumbing (dist.cu; libnccl is dlopen'ed on first use)
+int bh_dist_allreduce_sum(bh_ctx* ctx, double* buf_dev, int64_t count);
+int bh_dist_allgather(bh_ctx* ctx, const double* send_dev, double* recv_dev, int64_t count_per_rank);
 
 // host-side small dense symmetric eigen-decomposition (ascending; vectors in columns of v, column-major)
 void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::vector<double>& v);

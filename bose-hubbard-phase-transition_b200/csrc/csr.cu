@@ -478,7 +478,7 @@ static int export_matrix(bh_ctx* ctx, int mode, double cJ, double cU, double cmu
 
 extern "C" int bh_term_nnz(bh_ctx* ctx, int term, int64_t* nnz)
 {
-    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_term_nnz: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix || ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_term_nnz: call bh_setup first");
     if (!nnz || term < 0 || term > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_term_nnz: bad argument");
     *nnz = (term == BH_TERM_J) ? ctx->nnzJ : ctx->D;
     return BH_OK;
@@ -486,7 +486,7 @@ extern "C" int bh_term_nnz(bh_ctx* ctx, int term, int64_t* nnz)
 
 extern "C" int bh_hamiltonian_nnz(bh_ctx* ctx, int64_t* nnz)
 {
-    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_hamiltonian_nnz: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix || ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_hamiltonian_nnz: call bh_setup first");
     if (!nnz) return bh_fail(ctx, BH_ERR_ARG, "bh_hamiltonian_nnz: bad argument");
     *nnz = ctx->nnzH;
     return BH_OK;
@@ -494,7 +494,7 @@ extern "C" int bh_hamiltonian_nnz(bh_ctx* ctx, int64_t* nnz)
 
 extern "C" int bh_term_csc(bh_ctx* ctx, int term, double coef, int order, int32_t* outer, int32_t* inner, double* val)
 {
-    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_term_csc: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix || ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_term_csc: call bh_setup first");
     if (term < 0 || term > 2 || order < 0 || order > 2 || !outer || !inner || !val)
         return bh_fail(ctx, BH_ERR_ARG, "bh_term_csc: bad argument");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -523,7 +523,7 @@ extern "C" int bh_term_csc(bh_ctx* ctx, int term, double coef, int order, int32_
 extern "C" int bh_hamiltonian_csc(bh_ctx* ctx, double cJ, double cU, double cmu, int order, int32_t* outer,
                                   int32_t* inner, double* val)
 {
-    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_hamiltonian_csc: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix || ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_hamiltonian_csc: call bh_setup first");
     if (order < 0 || order > 2 || !outer || !inner || !val) return bh_fail(ctx, BH_ERR_ARG, "bh_hamiltonian_csc: bad argument");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     return export_matrix(ctx, EXPORT_HSUM, cJ, cU, cmu, order, outer, inner, val);
@@ -542,6 +542,8 @@ extern "C" int bh_load_matrix(bh_ctx* ctx, int64_t D, const int32_t* outer, cons
     bh_release_system(ctx);
     ctx->user_matrix = true;
     ctx->D = D;
+    ctx->row0 = 0;
+    ctx->nloc = D;
     ctx->ld = (D + 31) / 32 * 32;
     ctx->nnzH = nnz;
     ctx->nnzJ = nnz;

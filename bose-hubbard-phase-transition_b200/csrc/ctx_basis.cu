@@ -60,6 +60,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     ctx->own_stream = true;
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
     if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
+    if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
     if (const char* v = getenv("BH_REORTH_BLOCK")) { ctx->reorth_block = std::min(BH_MAX_NCV, std::max(1, atoi(v))); ctx->reorth_block_forced = true; }
     if (const char* v = getenv("BH_HV_STAGES")) ctx->hv_stages = std::min(4, std::max(2, atoi(v)));
     *out = ctx;
@@ -112,6 +113,9 @@ int bh_release_system(bh_ctx* ctx)
     ctx->m = ctx->n = 0;
     ctx->D = 0;
     ctx->user_matrix = false;
+    ctx->partitioned = false;
+    ctx->row0 = ctx->nloc = 0;
+    free_dev(ctx->d_xfull); ctx->d_xfull = nullptr;
     return BH_OK;
 }
 
@@ -171,14 +175,14 @@ extern "C" int bh_dimension(int m, int n, int64_t* D)
 
 // ---- K1 kernels ----
 // Thread k unranks state k: greedy descent through the table, site by site.
-__global__ void k_unrank(const BhTables* __restrict__ gtab, int64_t D, uint64_t* __restrict__ states,
+__global__ void k_unrank(const BhTables* __restrict__ gtab, int64_t row0, int64_t nloc, uint64_t* __restrict__ states,
                          double* __restrict__ dU)
 {
     __shared__ BhTables t;
     bh_stage_tables(&t, gtab);
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= D) return;
-    int rem = (int)k;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // local row; global rank = row0 + k
+    if (k >= nloc) return;
+    int rem = (int)(row0 + k);
     int Rprev = t.n;
     uint64_t s = 0;
     int u = 0;
@@ -316,9 +320,10 @@ int bh_build_basis(bh_ctx* ctx)
 
     BH_CUDA(ctx, cudaMalloc(&ctx->d_tab, sizeof(BhTables)));
     BH_H2D(ctx, ctx->d_tab, &t, sizeof(BhTables));
-    BH_CUDA(ctx, cudaMalloc(&ctx->d_states, sizeof(uint64_t) * ctx->D));
-    BH_CUDA(ctx, cudaMalloc(&ctx->d_dU, sizeof(double) * ctx->D));
-    k_unrank<<<nblocks(ctx->D, 256), 256, 0, ctx->stream>>>(ctx->d_tab, ctx->D, ctx->d_states, ctx->d_dU);
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_states, sizeof(uint64_t) * std::max<int64_t>(ctx->nloc, 1)));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_dU, sizeof(double) * std::max<int64_t>(ctx->nloc, 1)));
+    if (ctx->nloc > 0)
+        k_unrank<<<nblocks(ctx->nloc, 256), 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, ctx->nloc, ctx->d_states, ctx->d_dU);
     BH_LAUNCHED(ctx);
     BH_CUDA(ctx, cudaGetLastError());
     return BH_OK;
@@ -366,7 +371,7 @@ int bh_permute_vec(bh_ctx* ctx, int order, bool to_order, const double* src, dou
 {
     if (order == BH_ORDER_LEX) {
         if (src != dst)
-            BH_CUDA(ctx, cudaMemcpyAsync(dst, src, sizeof(double) * ctx->D, cudaMemcpyDeviceToDevice, ctx->stream));
+            BH_CUDA(ctx, cudaMemcpyAsync(dst, src, sizeof(double) * ctx->nloc, cudaMemcpyDeviceToDevice, ctx->stream));
         return BH_OK;
     }
     if (ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "a loaded matrix has only its own ordering (BH_ORDER_LEX)");
@@ -379,7 +384,7 @@ int bh_permute_vec(bh_ctx* ctx, int order, bool to_order, const double* src, dou
     return BH_OK;
 }
 
-extern "C" int bh_setup(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int* nbr_idx)
+static int setup_impl(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int* nbr_idx, bool partition)
 {
     if (!ctx) return BH_ERR_ARG;
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -399,12 +404,48 @@ extern "C" int bh_setup(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int
     ctx->m = m;
     ctx->n = n;
     ctx->D = D;
-    ctx->ld = (D + 31) / 32 * 32;
     ctx->nbr_ptr.assign(nbr_ptr, nbr_ptr + m + 1);
     ctx->nbr_idx.assign(nbr_idx, nbr_idx + nbr_ptr[m]);
+    if (partition && ctx->world > 1) {
+        // row partition for one large eigensolve: equal slices of the LEX rank range (the all-gather needs equal counts)
+        const int64_t per = ((D + ctx->world - 1) / ctx->world + 31) / 32 * 32;
+        ctx->row0 = std::min<int64_t>(D, per * ctx->rank);
+        ctx->nloc = std::min<int64_t>(D, ctx->row0 + per) - ctx->row0;
+        ctx->ld = per;
+        ctx->partitioned = true;
+        BH_TRY(bh_build_basis(ctx));
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_xfull, sizeof(double) * per * ctx->world));
+        BH_CUDA(ctx, cudaMemsetAsync(ctx->d_xfull, 0, sizeof(double) * per * ctx->world, ctx->stream));
+        BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return BH_OK;  // matrix-free only: no stored Hamiltonian
+    }
+    ctx->row0 = 0;
+    ctx->nloc = D;
+    ctx->ld = (D + 31) / 32 * 32;
     BH_TRY(bh_build_basis(ctx));
     BH_TRY(bh_build_hamiltonian(ctx));
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BH_OK;
+}
+
+extern "C" int bh_setup(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int* nbr_idx)
+{
+    return setup_impl(ctx, m, n, nbr_ptr, nbr_idx, false);
+}
+
+extern "C" int bh_setup_partitioned(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int* nbr_idx)
+{
+    if (!ctx) return BH_ERR_ARG;
+    if (ctx->world < 2) return bh_fail(ctx, BH_ERR_STATE, "bh_setup_partitioned: call bh_dist_init first");
+    return setup_impl(ctx, m, n, nbr_ptr, nbr_idx, true);
+}
+
+extern "C" int bh_partition(const bh_ctx* ctx, int64_t* row0, int64_t* nrows, int64_t* slice)
+{
+    if (!ctx || !ctx->D) return BH_ERR_STATE;
+    if (row0) *row0 = ctx->row0;
+    if (nrows) *nrows = ctx->nloc;
+    if (slice) *slice = ctx->ld;
     return BH_OK;
 }
 
@@ -425,7 +466,7 @@ int bh_ensure_staging(bh_ctx* ctx)
 
 extern "C" int bh_basis(bh_ctx* ctx, int order, double* tags, double* basis)
 {
-    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_basis: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix || ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_basis: call bh_setup first");
     if (order < 0 || order > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_basis: bad order");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t D = ctx->D;
@@ -450,7 +491,7 @@ extern "C" int bh_basis(bh_ctx* ctx, int order, double* tags, double* basis)
 
 extern "C" int bh_rank(bh_ctx* ctx, int order, const double* states, int64_t count, int32_t* ranks)
 {
-    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_rank: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix || ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_rank: call bh_setup first");
     if (order < 0 || order > 2 || !states || !ranks || count < 0) return bh_fail(ctx, BH_ERR_ARG, "bh_rank: bad argument");
     if (count == 0) return BH_OK;
     BH_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -236,15 +236,16 @@ k_hv_sell(int64_t D, int64_t nslices, const int* __restrict__ sptr, const int* _
 // ---------------------------------------------------------------------------------------------
 template <int M>
 __global__ void __launch_bounds__(256)
-k_hv_free(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restrict__ states,
+k_hv_free(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
           const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
           double* __restrict__ y)
 {
     __shared__ BhTables t;
     bh_stage_tables(&t, gtab);
     const double shift = __dmul_rn(-(double)t.n, cmu);
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < D; k += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t s = states[k];
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = row0 + l;  // global LEX rank; states / dU / y are local, x is the full vector
+        const uint64_t s = states[l];
         int dn[M], up[M];
         bh_rank_prefix<M>(t, s, dn, up);
         double acc = 0.0;
@@ -261,12 +262,12 @@ k_hv_free(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restri
                 acc += (double)w * t.sq[(bh_occ(s, dst) + 1) * ns] * __ldg(x + tgt);
             }
         }
-        const double diag = __dadd_rn(__dmul_rn(dU[k], cU), shift);
-        y[k] = diag * x[k] - cJ * acc;
+        const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
+        y[l] = diag * x[k] - cJ * acc;
     }
 }
 
-typedef void (*hv_free_fn_t)(const BhTables*, int64_t, const uint64_t*, const double*, double, double, double,
+typedef void (*hv_free_fn_t)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double, double, double,
                              const double*, double*);
 
 // K4, bond-list variant: the per-thread rank prefixes live in shared memory ([site][thread], conflict-free),
@@ -274,7 +275,7 @@ typedef void (*hv_free_fn_t)(const BhTables*, int64_t, const uint64_t*, const do
 // pairs, and one kernel serves every m.  ~4x fewer instructions per row than the unrolled variant.
 #define HVF_THREADS 256
 __global__ void __launch_bounds__(HVF_THREADS)
-k_hv_free_bonds(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restrict__ states,
+k_hv_free_bonds(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
                 const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
                 double* __restrict__ y)
 {
@@ -285,8 +286,9 @@ k_hv_free_bonds(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __
     const int tid = threadIdx.x;
     const int m = t.m, nb = t.nbonds;
     const double shift = __dmul_rn(-(double)t.n, cmu);
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + tid; k < D; k += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t s = states[k];
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + tid; l < D; l += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = row0 + l;
+        const uint64_t s = states[l];
         int R = t.n, adn = 0, aup = 0;
         for (int q = 0; q < m; ++q) {
             sdn[q][tid] = adn;
@@ -308,8 +310,8 @@ k_hv_free_bonds(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __
             const double xv = ns ? __ldg(x + (int)k + delta) : 0.0;
             acc = fma((double)w * t.sq[(bh_occ(s, dst) + 1) * ns], xv, acc);
         }
-        const double diag = __dadd_rn(__dmul_rn(dU[k], cU), shift);
-        y[k] = diag * x[k] - cJ * acc;
+        const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
+        y[l] = diag * x[k] - cJ * acc;
     }
 }
 
@@ -319,15 +321,16 @@ k_hv_free_bonds(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __
 // bond uses the accumulated totals.  ~3x fewer instructions per row than the bond-list kernel.
 template <int M, bool CLOSED>
 __global__ void __launch_bounds__(256)
-k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restrict__ states,
+k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
                 const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
                 double* __restrict__ y)
 {
     __shared__ BhTables t;
     bh_stage_tables(&t, gtab);
     const double shift = __dmul_rn(-(double)t.n, cmu);
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < D; k += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t s = states[k];
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = row0 + l;
+        const uint64_t s = states[l];
         const double* xk = x + k;
         const int n0 = bh_occ(s, 0);
         int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
@@ -354,8 +357,8 @@ k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __
             acc = fma(t.sq[(n0 + 1) * nl], xa, acc);
             acc = fma(t.sq[(nl + 1) * n0], xb, acc);
         }
-        const double diag = __dadd_rn(__dmul_rn(dU[k], cU), shift);
-        y[k] = diag * x[k] - (2.0 * cJ) * acc;
+        const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
+        y[l] = diag * x[k] - (2.0 * cJ) * acc;
     }
 }
 
@@ -381,7 +384,7 @@ static hv_free_fn_t hv_chain_kernel(int m)
     return nullptr;
 }
 
-typedef void (*hv_free_fn)(const BhTables*, int64_t, const uint64_t*, const double*, double, double, double,
+typedef void (*hv_free_fn)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double, double, double,
                            const double*, double*);
 
 static hv_free_fn hv_free_kernel(int m)
@@ -410,6 +413,8 @@ static hv_free_fn hv_free_kernel(int m)
 int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x, double* y, double)
 {
     const int64_t D = ctx->D;
+    if (ctx->partitioned && kernel != BH_HV_MATRIX_FREE)
+        return bh_fail(ctx, BH_ERR_STATE, "a row-partitioned context has no stored matrix: use BH_HV_MATRIX_FREE");
     if (ctx->user_matrix != (kernel == BH_HV_USER))
         return bh_fail(ctx, BH_ERR_STATE, "kernel BH_HV_USER needs bh_load_matrix, the other kernels need bh_setup");
     if (kernel == BH_HV_USER || (kernel == BH_HV_STORED && ctx->hv_variant == 2)) {
@@ -461,19 +466,28 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, cons
             BH_LAUNCHED(ctx);
         }
     } else if (kernel == BH_HV_MATRIX_FREE) {
-        if (ctx->free_variant == 1 && ctx->h_tab.chain) {
-            hv_free_fn_t fn = (ctx->h_tab.chain == 2) ? hv_chain_kernel<true>(ctx->m) : hv_chain_kernel<false>(ctx->m);
-            int grid = (int)std::min<int64_t>(nblocks(D, 256), (int64_t)ctx->sm_count * 8);
-            fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x, y);
-        } else if (ctx->free_variant >= 1) {
-            int grid = (int)std::min<int64_t>(nblocks(D, HVF_THREADS), (int64_t)ctx->sm_count * 5);
-            k_hv_free_bonds<<<grid, HVF_THREADS, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x, y);
-        } else {
-            hv_free_fn fn = hv_free_kernel(ctx->m);
-            int grid = (int)std::min<int64_t>(nblocks(D, 256), (int64_t)ctx->sm_count * 8);
-            fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x, y);
+        // row-partitioned context: x is the local slice; exchange it (NCCL all-gather) and read the full vector
+        const double* xin = x;
+        const int64_t nloc = ctx->nloc;
+        if (ctx->partitioned) {
+            BH_TRY(bh_dist_allgather(ctx, x, ctx->d_xfull, ctx->ld));
+            xin = ctx->d_xfull;
         }
-        BH_LAUNCHED(ctx);
+        if (nloc > 0) {
+            if (ctx->free_variant == 1 && ctx->h_tab.chain) {
+                hv_free_fn_t fn = (ctx->h_tab.chain == 2) ? hv_chain_kernel<true>(ctx->m) : hv_chain_kernel<false>(ctx->m);
+                int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
+                fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y);
+            } else if (ctx->free_variant >= 1) {
+                int grid = (int)std::min<int64_t>(nblocks(nloc, HVF_THREADS), (int64_t)ctx->sm_count * 5);
+                k_hv_free_bonds<<<grid, HVF_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y);
+            } else {
+                hv_free_fn fn = hv_free_kernel(ctx->m);
+                int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
+                fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y);
+            }
+            BH_LAUNCHED(ctx);
+        }
     } else {
         return bh_fail(ctx, BH_ERR_ARG, "unknown H.v kernel");
     }
@@ -493,6 +507,7 @@ extern "C" int bh_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, 
 {
     if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_hv: call bh_setup first");
     if (!x || !y || order < 0 || order > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_hv: bad argument");
+    if (ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_hv: use bh_hv_dev with the local slice on a row-partitioned context");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     BH_TRY(bh_ensure_staging(ctx));
     BH_TRY(bh_ensure_workspace(ctx, 0));
@@ -521,14 +536,14 @@ extern "C" int bh_hv_algorithmic_bytes(bh_ctx* ctx, int kernel, int64_t* bytes)
 // element i = seed_{i+1} / (2^31 - 1) - 0.5.  Each thread jumps ahead by modular exponentiation.
 // ---------------------------------------------------------------------------------------------
 #define LCG_CHUNK 64
-__global__ void k_lcg_fill(int64_t n, double* __restrict__ out)
+__global__ void k_lcg_fill(int64_t first, int64_t n, double* __restrict__ out)
 {
     const unsigned long long M = 2147483647ull;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t start = c * LCG_CHUNK;
     if (start >= n) return;
     unsigned long long seed = 1, base = 16807ull;
-    for (unsigned long long p = (unsigned long long)start; p; p >>= 1) {
+    for (unsigned long long p = (unsigned long long)(first + start); p; p >>= 1) {
         if (p & 1) seed = seed * base % M;
         base = base * base % M;
     }
@@ -544,7 +559,9 @@ extern "C" int bh_lcg_fill_dev(bh_ctx* ctx, double* x_dev, int64_t count)
     if (!ctx || !x_dev || count < 0) return bh_fail(ctx, BH_ERR_ARG, "bh_lcg_fill_dev: bad argument");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     if (count == 0) return BH_OK;
-    k_lcg_fill<<<nblocks((count + LCG_CHUNK - 1) / LCG_CHUNK, 128), 128, 0, ctx->stream>>>(count, x_dev);
+    // a row-partitioned context fills its slice of the one global sequence
+    const int64_t first = ctx->partitioned ? ctx->row0 : 0;
+    k_lcg_fill<<<nblocks((count + LCG_CHUNK - 1) / LCG_CHUNK, 128), 128, 0, ctx->stream>>>(first, count, x_dev);
     BH_LAUNCHED(ctx);
     BH_CUDA(ctx, cudaGetLastError());
     return BH_OK;

@@ -14,6 +14,8 @@
 // stay in HBM; a Lanczos step is 7 launches with no host synchronisation (each reduction kernel finishes
 // in its last-arriving block, deterministically); the host reads the ncv-sized scalar arrays once per
 // restart, solves the <=128 x 128 projected problem and uploads the Ritz coefficients.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -34,6 +36,7 @@
 #define GT_CH 8  // columns accumulated per sweep of the transposed product
 
 static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
+namespace cg = cooperative_groups;
 
 __device__ __forceinline__ bool bh_last_block(unsigned int* counter)
 {
@@ -48,7 +51,7 @@ __device__ __forceinline__ bool bh_last_block(unsigned int* counter)
 // |v| -> scal[dst]  (used once for |A v0|)
 __global__ void __launch_bounds__(VEC_THREADS)
 k_norm(int64_t D, const double* __restrict__ v, double* __restrict__ scal, int dst, double* __restrict__ part,
-       unsigned int* __restrict__ counter)
+       unsigned int* __restrict__ counter, int raw = 0)
 {
     __shared__ double scratch[32];
     double acc = 0.0;
@@ -60,7 +63,7 @@ k_norm(int64_t D, const double* __restrict__ v, double* __restrict__ scal, int d
         double t = 0.0;
         for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += part[b];
         t = bh_block_sum(t, scratch);
-        if (threadIdx.x == 0) scal[dst] = sqrt(t);
+        if (threadIdx.x == 0) scal[dst] = raw ? t : sqrt(t);  // raw: local sum of squares, all-reduced by the caller
     }
 }
 
@@ -142,7 +145,8 @@ k_resid_norm(int64_t D, const double* __restrict__ w, const double* __restrict__
 template <bool MULTI>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_gemv_t(int64_t D, int64_t ld, const double* __restrict__ V, int col0, int cnt, const double* __restrict__ f,
-         double* __restrict__ scal, int i, int fix_offd, double* __restrict__ part, unsigned int* __restrict__ counter)
+         double* __restrict__ scal, int i, int fix_offd, double* __restrict__ part, unsigned int* __restrict__ counter,
+         int raw = 0)
 {
     __shared__ double red[VEC_THREADS / 32][GT_CH];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -188,8 +192,8 @@ k_gemv_t(int64_t D, int64_t ld, const double* __restrict__ V, int col0, int cnt,
             if (lane == 0) {
                 const int c = col0 + j;
                 scal[S_VF + c] = t;
-                if (c == i) scal[S_ALPHA + i] += t;
-                if (fix_offd && c == i - 1) scal[S_OFFD + i] += t;
+                if (!raw && c == i) scal[S_ALPHA + i] += t;
+                if (!raw && fix_offd && c == i - 1) scal[S_OFFD + i] += t;
             }
         }
     }
@@ -199,7 +203,7 @@ k_gemv_t(int64_t D, int64_t ld, const double* __restrict__ V, int col0, int cnt,
 template <bool MULTI>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_gemv_n_norm(int64_t D, int64_t ld, const double* __restrict__ V, int col0, int cnt, double* __restrict__ f,
-              double* __restrict__ scal, int i, double* __restrict__ part, unsigned int* __restrict__ counter)
+              double* __restrict__ scal, int i, double* __restrict__ part, unsigned int* __restrict__ counter, int raw = 0)
 {
     __shared__ double scratch[32];
     __shared__ double coef[MULTI ? NC : GT_CH];
@@ -240,7 +244,217 @@ k_gemv_n_norm(int64_t D, int64_t ld, const double* __restrict__ V, int col0, int
         double t = 0.0;
         for (int bb = threadIdx.x; bb < (int)gridDim.x; bb += blockDim.x) t += part[bb];
         t = bh_block_sum(t, scratch);
-        if (threadIdx.x == 0) scal[S_BETA + i + 1] = sqrt(t);
+        if (threadIdx.x == 0) {
+            if (raw) scal[S_FLAG + 3] = t; else scal[S_BETA + i + 1] = sqrt(t);
+        }
+    }
+}
+
+
+// ---- row-partitioned solve: local raw sums are all-reduced (NCCL), then these one-thread kernels finish ----
+__global__ void k_fin_sqrt(double* __restrict__ scal, int src, int dst) { scal[dst] = sqrt(scal[src]); }
+__global__ void k_fin_coef(double* __restrict__ scal, int i, int pass)
+{
+    // classical Gram-Schmidt twice against all columns: T(i,i) and T(i,i-1) are the accumulated coefficients
+    const double a = scal[S_VF + i], o = (i > 0) ? scal[S_VF + i - 1] : 0.0;
+    if (pass == 0) {
+        scal[S_ALPHA + i] = a;
+        scal[S_OFFD + i] = o;
+    } else {
+        scal[S_ALPHA + i] += a;
+        scal[S_OFFD + i] += o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One Lanczos step after the H.v in ONE cooperative launch (used when the residual fits in registers:
+// <= COOP_NP row pairs per thread).  The kernel keeps the residual in registers from the three-term update to
+// the final normalisation:
+//   w -= beta v_{i-1};  alpha = v_i.w            -> grid.sync
+//   f  = w - alpha v_i
+//   for each block of 8 basis columns:  c = V_B^T f -> grid.sync ;  f -= V_B c     (block MGS, V_B re-read from L2)
+//   beta' = |f|                                   -> grid.sync
+//   f -> memory,  v_{i+1} = f / beta'             (the next step's scaling pass is fused here)
+// i.e. 2 launches per Lanczos step instead of 9-15, no f round-trips through HBM, and the basis streamed once.
+// All partial sums are combined in a fixed order (deterministic).
+// ---------------------------------------------------------------------------------------------------------
+#define COOP_NP 10
+#define COOP_THREADS 256
+
+__device__ __forceinline__ double coop_sum_partials(const double* __restrict__ part, int n, int stride)
+{
+    // warp-level: lanes stride over n partials spaced `stride` doubles apart, then a fixed shuffle tree
+    double t = 0.0;
+    for (int b = threadIdx.x & 31; b < n; b += 32) t += part[(int64_t)b * stride];
+    return bh_warp_sum(t);
+}
+
+__global__ void __launch_bounds__(COOP_THREADS, 2)
+k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, int passes, const double* __restrict__ w,
+            double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[COOP_THREADS / 32][GT_CH];
+    __shared__ double cs[GT_CH];
+    __shared__ double sh_val;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nblk = gridDim.x;
+    const int64_t npair = (D + 1) >> 1, ld2 = ld >> 1;
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double* part_a = part;                         // [nblk]
+    double* part_n = part + nblk;                  // [nblk]
+    double* part_c = part + 2 * (int64_t)nblk;     // [2][nblk][GT_CH]
+    const double2* w2 = reinterpret_cast<const double2*>(w);
+    const double2* vi2 = reinterpret_cast<const double2*>(V + (int64_t)i * ld);
+    const double2* vp2 = reinterpret_cast<const double2*>(V + (int64_t)(i > 0 ? i - 1 : 0) * ld);
+    const double2* V2 = reinterpret_cast<const double2*>(V);
+
+    // ---- three-term update and alpha ----
+    const double b = subtract ? scal[S_BETA + i] : 0.0;
+    double2 fr[COOP_NP];
+    double acc0 = 0.0;
+#pragma unroll
+    for (int t = 0; t < COOP_NP; ++t) {
+        const int64_t p = gtid + t * gsz;
+        fr[t] = make_double2(0.0, 0.0);
+        if (p < npair) {
+            double2 wr = w2[p];
+            if (subtract) {
+                const double2 vp = vp2[p];
+                wr.x = fma(-b, vp.x, wr.x);
+                wr.y = fma(-b, vp.y, wr.y);
+            }
+            const double2 v = vi2[p];
+            acc0 = fma(v.x, wr.x, fma(v.y, wr.y, acc0));
+            fr[t] = wr;
+        }
+    }
+    acc0 = bh_warp_sum(acc0);
+    if (lane == 0) red[wid][0] = acc0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < COOP_THREADS / 32; ++q) t += red[q][0];
+        part_a[blockIdx.x] = t;
+    }
+    grid.sync();
+    if (wid == 0) {
+        const double a = coop_sum_partials(part_a, nblk, 1);
+        if (lane == 0) sh_val = a;
+    }
+    __syncthreads();
+    double alpha = sh_val;
+#pragma unroll
+    for (int t = 0; t < COOP_NP; ++t) {
+        const int64_t p = gtid + t * gsz;
+        if (p < npair) {
+            const double2 v = vi2[p];
+            fr[t].x = fma(-alpha, v.x, fr[t].x);
+            fr[t].y = fma(-alpha, v.y, fr[t].y);
+        }
+    }
+
+    // ---- block modified Gram-Schmidt against columns 0..i ----
+    double offd = b;
+    int buf = 0;
+    for (int pass = 0; pass < passes; ++pass) {
+        for (int c0 = 0; c0 <= i; c0 += GT_CH) {
+            const int nc = min(GT_CH, i + 1 - c0);
+            const double2* VB = V2 + (int64_t)c0 * ld2;
+            double acc[GT_CH];
+#pragma unroll
+            for (int j = 0; j < GT_CH; ++j) acc[j] = 0.0;
+#pragma unroll
+            for (int t = 0; t < COOP_NP; ++t) {
+                const int64_t p = gtid + t * gsz;
+                if (p < npair) {
+                    double2 v[GT_CH];
+#pragma unroll
+                    for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int j = 0; j < GT_CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < GT_CH; ++j) acc[j] = bh_warp_sum(acc[j]);
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < GT_CH; ++j) red[wid][j] = acc[j];
+            }
+            __syncthreads();
+            double* pc = part_c + (int64_t)buf * nblk * GT_CH;
+            if (threadIdx.x < GT_CH) {
+                double t = 0.0;
+                for (int q = 0; q < COOP_THREADS / 32; ++q) t += red[q][threadIdx.x];
+                pc[(int64_t)blockIdx.x * GT_CH + threadIdx.x] = t;
+            }
+            grid.sync();
+            if (wid < nc) {
+                const double c = coop_sum_partials(pc + wid, nblk, GT_CH);
+                if (lane == 0) cs[wid] = c;
+            } else if (wid < GT_CH && lane == 0) {
+                cs[wid] = 0.0;
+            }
+            __syncthreads();
+            double c[GT_CH];
+#pragma unroll
+            for (int j = 0; j < GT_CH; ++j) c[j] = cs[j];
+            if (i >= c0 && i < c0 + GT_CH) alpha += cs[i - c0];                         // Lanczos.h:170
+            if (subtract && i - 1 >= c0 && i - 1 < c0 + GT_CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
+#pragma unroll
+            for (int t = 0; t < COOP_NP; ++t) {
+                const int64_t p = gtid + t * gsz;
+                if (p < npair) {
+                    double2 v[GT_CH];
+#pragma unroll
+                    for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int j = 0; j < GT_CH; ++j) {
+                        fr[t].x = fma(-v[j].x, c[j], fr[t].x);
+                        fr[t].y = fma(-v[j].y, c[j], fr[t].y);
+                    }
+                }
+            }
+            buf ^= 1;
+            __syncthreads();  // cs / red are rewritten by the next block of columns
+        }
+    }
+
+    // ---- norm, write-back, next basis vector ----
+    double nrm = 0.0;
+#pragma unroll
+    for (int t = 0; t < COOP_NP; ++t) nrm = fma(fr[t].x, fr[t].x, fma(fr[t].y, fr[t].y, nrm));
+    nrm = bh_warp_sum(nrm);
+    if (lane == 0) red[wid][0] = nrm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < COOP_THREADS / 32; ++q) t += red[q][0];
+        part_n[blockIdx.x] = t;
+    }
+    grid.sync();
+    if (wid == 0) {
+        const double t = coop_sum_partials(part_n, nblk, 1);
+        if (lane == 0) sh_val = sqrt(t);
+    }
+    __syncthreads();
+    const double beta = sh_val;
+    const double inv = (beta > thresh) ? 1.0 / beta : 0.0;
+    double2* f2 = reinterpret_cast<double2*>(f);
+    double2* vn2 = reinterpret_cast<double2*>(V + (int64_t)(i + 1) * ld);
+#pragma unroll
+    for (int t = 0; t < COOP_NP; ++t) {
+        const int64_t p = gtid + t * gsz;
+        if (p < npair) {
+            f2[p] = fr[t];
+            vn2[p] = make_double2(fr[t].x * inv, fr[t].y * inv);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[S_ALPHA + i] = alpha;
+        scal[S_OFFD + i] = offd;
+        scal[S_BETA + i + 1] = beta;
+        if (!(beta > thresh)) scal[S_FLAG] = 1.0;
     }
 }
 
@@ -330,10 +544,12 @@ int bh_ensure_workspace(bh_ctx* ctx, int ncv)
 int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
                BhSolve* out)
 {
-    const int64_t D = ctx->D, ld = ctx->ld;
+    const int64_t Dglobal = ctx->D, ld = ctx->ld;
+    const int64_t D = ctx->nloc;  // rows held by this context (all of them unless the solve is row-partitioned)
+    const bool dist = ctx->partitioned && ctx->world > 1;
     // Spectra::GenEigsBase constructor checks (GenEigsBase.h:335-339), which the reference relies on
-    if (nev < 1 || nev > D - 2) return bh_fail(ctx, BH_ERR_ARG, "nev must satisfy 1 <= nev <= n - 2, n is the size of matrix");
-    if (ncv < nev + 2 || ncv > D) return bh_fail(ctx, BH_ERR_ARG, "ncv must satisfy nev + 2 <= ncv <= n, n is the size of matrix");
+    if (nev < 1 || nev > Dglobal - 2) return bh_fail(ctx, BH_ERR_ARG, "nev must satisfy 1 <= nev <= n - 2, n is the size of matrix");
+    if (ncv < nev + 2 || ncv > Dglobal) return bh_fail(ctx, BH_ERR_ARG, "ncv must satisfy nev + 2 <= ncv <= n, n is the size of matrix");
     if (ncv > BH_MAX_NCV) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "ncv exceeds BH_MAX_NCV");
     const auto t_start = std::chrono::steady_clock::now();
     BH_TRY(bh_ensure_workspace(ctx, ncv));
@@ -342,7 +558,7 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
     double* scal = ctx->d_scal;
     double* part = ctx->d_part;
     unsigned int* counter = ctx->d_counter;
-    const int G = (int)std::min<int64_t>(nblocks(D, VEC_THREADS), (int64_t)ctx->sm_count * 4);
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(D, VEC_THREADS), (int64_t)ctx->sm_count * 4));
     const double eps = std::numeric_limits<double>::epsilon();
     const double near0 = std::numeric_limits<double>::min() * 10.0;
     const double eps23 = std::pow(eps, 2.0 / 3.0);
@@ -351,7 +567,13 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
     // v0 = LCG ; f = A v0 ; beta[0] = |f|   (Arnoldi.h:147-154)
     BH_TRY(bh_lcg_fill_dev(ctx, ctx->d_w, D));
     BH_TRY(bh_launch_hv(ctx, cJ, cU, cmu, kernel, ctx->d_w, ctx->d_f));
-    k_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, scal, S_BETA + 0, part, counter);
+    if (dist) {
+        k_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, scal, S_FLAG + 3, part, counter, 1);
+        BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_FLAG + 3, 1));
+        k_fin_sqrt<<<1, 1, 0, st>>>(scal, S_FLAG + 3, S_BETA + 0);
+    } else {
+        k_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, scal, S_BETA + 0, part, counter);
+    }
     BH_LAUNCHED(ctx);
     int nmatvec = 1;
 
@@ -372,18 +594,63 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
             BH_CUDA(ctx, cudaFuncSetAttribute(k_compress<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compress_smem));
     }
 
+    // cooperative single-launch step: needs every CTA resident and <= COOP_NP row pairs per thread
+    int coop_grid = 0;
+    if (ctx->coop && !dist) {
+        int bps = 0;
+        BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop, COOP_THREADS, 0));
+        bps = std::min(bps, 2);
+        const int64_t npair = (D + 1) / 2;
+        if (bps >= 1 && npair <= (int64_t)ctx->sm_count * bps * COOP_THREADS * COOP_NP) {
+            coop_grid = ctx->sm_count * bps;
+            // do not spread a tiny problem over idle CTAs: grid syncs cost more with more CTAs
+            const int64_t need = (npair + COOP_THREADS - 1) / COOP_THREADS;
+            if (need < coop_grid) coop_grid = (int)std::max<int64_t>(need, 1);
+        }
+    }
+
     for (;;) {
         for (int i = from; i < ncv; ++i) {
             double* vi = V + (int64_t)i * ld;
             const bool first_after_restart = (from > 0 && i == from);
-            k_scale<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, vi, scal, i, near0);
+            // v_i = f / beta: written by the previous cooperative step except at the start of a cycle
+            if (!coop_grid || i == from) {
+                k_scale<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, vi, scal, i, near0);
+                BH_LAUNCHED(ctx);
+            }
             BH_TRY(bh_launch_hv(ctx, cJ, cU, cmu, kernel, vi, ctx->d_w));
             ++nmatvec;
             const int subtract = (i > 0 && !first_after_restart) ? 1 : 0;
+            if (dist) {
+                // classical Gram-Schmidt twice against every column (it subsumes the three-term recurrence and the
+                // coupling row after a restart); 4 small all-reduces per step
+                std::swap(ctx->d_w, ctx->d_f);  // the residual is built in place in what H.v just wrote
+                for (int pass = 0; pass < 2; ++pass) {
+                    k_gemv_t<true><<<G, VEC_THREADS, 0, st>>>(D, ld, V, 0, i + 1, ctx->d_f, scal, i, 0, part, counter, 1);
+                    BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_VF, i + 1));
+                    k_fin_coef<<<1, 1, 0, st>>>(scal, i, pass);
+                    k_gemv_n_norm<true><<<G, VEC_THREADS, 0, st>>>(D, ld, V, 0, i + 1, ctx->d_f, scal, i, part, counter, 1);
+                    BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_FLAG + 3, 1));
+                }
+                k_fin_sqrt<<<1, 1, 0, st>>>(scal, S_FLAG + 3, S_BETA + i + 1);
+                ctx->launches += 8;
+                continue;
+            }
+            if (coop_grid) {
+                int ii = i, sub = subtract, npass = first_after_restart ? 2 : 1;
+                int64_t Dv = D, ldv = ld;
+                const double* wv = ctx->d_w;
+                double* fv = ctx->d_f;
+                double th = near0;
+                void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th};
+                BH_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_coop, dim3(coop_grid), dim3(COOP_THREADS), args, 0, st));
+                BH_LAUNCHED(ctx);
+                continue;
+            }
             k_local_alpha<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_w, i > 0 ? vi - ld : vi, vi, scal, i, subtract, part, counter);
             k_resid_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_w, vi, ctx->d_f, scal, i, part, counter);
             const int passes = first_after_restart ? 2 : 1;
-            int nlaunch = 3;
+            int nlaunch = 2;
             for (int p = 0; p < passes; ++p) {
                 for (int c0 = 0; c0 <= i; c0 += rblock) {
                     const int cnt = std::min(rblock, i + 1 - c0);
@@ -464,10 +731,17 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
 int bh_ritz_vector(bh_ctx* ctx, const BhSolve& s, int col, double* x_dev)
 {
     BH_H2D(ctx, ctx->d_small, s.Y.data() + (size_t)col * s.ncv, sizeof(double) * s.ncv);
-    const int G = (int)std::min<int64_t>(nblocks(ctx->D, VEC_THREADS), (int64_t)ctx->sm_count * 4);
-    k_lincomb<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->D, ctx->ld, ctx->d_V, s.ncv, ctx->d_small, x_dev);
-    k_norm<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->D, x_dev, ctx->d_scal, S_VF, ctx->d_part, ctx->d_counter);
-    k_scale_inplace<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->D, x_dev, ctx->d_scal, S_VF);
+    const int64_t n = ctx->nloc;
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(n, VEC_THREADS), (int64_t)ctx->sm_count * 4));
+    k_lincomb<<<G, VEC_THREADS, 0, ctx->stream>>>(n, ctx->ld, ctx->d_V, s.ncv, ctx->d_small, x_dev);
+    if (ctx->partitioned && ctx->world > 1) {
+        k_norm<<<G, VEC_THREADS, 0, ctx->stream>>>(n, x_dev, ctx->d_scal, S_FLAG + 3, ctx->d_part, ctx->d_counter, 1);
+        BH_TRY(bh_dist_allreduce_sum(ctx, ctx->d_scal + S_FLAG + 3, 1));
+        k_fin_sqrt<<<1, 1, 0, ctx->stream>>>(ctx->d_scal, S_FLAG + 3, S_VF);
+    } else {
+        k_norm<<<G, VEC_THREADS, 0, ctx->stream>>>(n, x_dev, ctx->d_scal, S_VF, ctx->d_part, ctx->d_counter);
+    }
+    k_scale_inplace<<<G, VEC_THREADS, 0, ctx->stream>>>(n, x_dev, ctx->d_scal, S_VF);
     ctx->launches += 3;
     BH_CUDA(ctx, cudaGetLastError());
     return BH_OK;
@@ -478,6 +752,7 @@ extern "C" int bh_eigs(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, i
 {
     if (!ctx || !ctx->D) return bh_fail(ctx, BH_ERR_STATE, "bh_eigs: call bh_setup first");
     if (!evals || order < 0 || order > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_eigs: bad argument");
+    if (ctx->partitioned && order != BH_ORDER_LEX) return bh_fail(ctx, BH_ERR_ARG, "bh_eigs: a row-partitioned context returns LEX-order slices only");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     BhSolve s;
     const int rc = bh_lanczos(ctx, cJ, cU, cmu, nev, ncv, tol, maxit, kernel, &s);
@@ -489,7 +764,7 @@ extern "C" int bh_eigs(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, i
         for (int c = 0; c < nev; ++c) {
             BH_TRY(bh_ritz_vector(ctx, s, c, ctx->d_x));
             BH_TRY(bh_permute_vec(ctx, order, true, ctx->d_x, ctx->d_y));
-            BH_D2H(ctx, evecs + (size_t)c * ctx->D, ctx->d_y, sizeof(double) * ctx->D);
+            BH_D2H(ctx, evecs + (size_t)c * ctx->nloc, ctx->d_y, sizeof(double) * ctx->nloc);
             BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
     }

@@ -18,8 +18,8 @@ static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); 
 
 template <int M>
 __global__ void __launch_bounds__(SPDM_THREADS)
-k_spdm(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restrict__ states, const double* __restrict__ phi,
-       double* __restrict__ part /* [gridDim.x][M][M] */)
+k_spdm(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
+       const double* __restrict__ phi /* full vector, indexed by global LEX rank */, double* __restrict__ part /* [gridDim.x][M][M] */)
 {
     __shared__ BhTables t;
     __shared__ double scratch[32];
@@ -29,10 +29,11 @@ k_spdm(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restrict_
     double acc[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) acc[i] = 0.0;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < D; k += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = row0 + l;
         const double pk = phi[k];
         if (!(fabs(pk) > eps)) continue;
-        const uint64_t s = states[k];
+        const uint64_t s = states[l];
         const int nj = bh_occ(s, j);
         if (nj < 1) continue;
         int dn[M], up[M];
@@ -71,7 +72,7 @@ __global__ void k_spdm_reduce(int m, int nb, const double* __restrict__ part, do
     rho[j + i * m] = t;
 }
 
-typedef void (*spdm_fn)(const BhTables*, int64_t, const uint64_t*, const double*, double*);
+typedef void (*spdm_fn)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double*);
 static spdm_fn spdm_kernel(int m)
 {
     switch (m) {
@@ -99,14 +100,22 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
 {
     const int m = ctx->m;
     BH_TRY(bh_ensure_workspace(ctx, 0));
-    const int gx = (int)std::min<int64_t>(nblocks(ctx->D, SPDM_THREADS), (int64_t)ctx->sm_count * 2);
+    const int64_t nloc = ctx->nloc;
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(nloc, SPDM_THREADS), (int64_t)ctx->sm_count * 2));
     double* d_part = nullptr;
     double* d_rho = nullptr;
     BH_CUDA(ctx, cudaMalloc(&d_part, sizeof(double) * (size_t)gx * m * m));
     BH_CUDA(ctx, cudaMalloc(&d_rho, sizeof(double) * m * m));
+    const bool dist = ctx->partitioned && ctx->world > 1;
+    const double* phi_full = phi_dev;
+    if (dist) {  // phi_dev is the local slice: exchange it once, reduce the local partial matrices afterwards
+        BH_TRY(bh_dist_allgather(ctx, phi_dev, ctx->d_xfull, ctx->ld));
+        phi_full = ctx->d_xfull;
+    }
     dim3 grid(gx, m);
-    spdm_kernel(m)<<<grid, SPDM_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->D, ctx->d_states, phi_dev, d_part);
+    spdm_kernel(m)<<<grid, SPDM_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, phi_full, d_part);
     k_spdm_reduce<<<1, m * m, 0, ctx->stream>>>(m, gx, d_part, 1.0 / (double)ncols, d_rho);
+    if (dist) BH_TRY(bh_dist_allreduce_sum(ctx, d_rho, m * m));
     ctx->launches += 2;
     BH_CUDA(ctx, cudaGetLastError());
     BH_D2H(ctx, rho_host, d_rho, sizeof(double) * m * m);
@@ -118,7 +127,7 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
 
 extern "C" int bh_spdm(bh_ctx* ctx, int order, const double* phi, int ncols, double* rho)
 {
-    if (!ctx || !ctx->D || ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "bh_spdm: call bh_setup first");
+    if (!ctx || !ctx->D || ctx->user_matrix || ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_spdm: call bh_setup first (host vectors are not accepted on a row-partitioned context)");
     if (!phi || !rho || ncols < 1 || order < 0 || order > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_spdm: bad argument");
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     BH_TRY(bh_ensure_staging(ctx));

@@ -128,6 +128,20 @@ int bh_point(bh_ctx* ctx, double cJ, double cU, double cmu, int nb_eigen, int ke
 int bh_points(bh_ctx* ctx, const double* cJ, const double* cU, const double* cmu, int64_t npoints, int nb_eigen,
               int kernel, double* out3, bh_eigs_info* infos /* may be NULL */);
 
+/* ---- one large eigensolve row-partitioned over several GPUs (BASELINE.json config 5) ---------------------
+ * One process (or thread) per GPU.  Rank 0 creates a 128-byte NCCL id (bh_dist_unique_id) and hands it to the
+ * others by any means (the Python driver broadcasts it with torch.distributed); every rank calls bh_dist_init on
+ * its context, then bh_setup_partitioned: the context owns an equal slice of the LEX rank range, holds only
+ * that slice of every vector, applies H matrix-free after an ncclAllGather of the Lanczos vector and
+ * ncclAllReduces the recurrence scalars.  bh_eigs / bh_point then work as on one GPU with
+ * kernel = BH_HV_MATRIX_FREE and order = BH_ORDER_LEX; eigenvectors come back as the local slice
+ * (nrows rows per column, column stride = nrows).  No collective is issued outside these calls. */
+int bh_dist_unique_id(void* id128);
+int bh_dist_init(bh_ctx* ctx, int world, int rank, const void* id128);
+int bh_dist_finalize(bh_ctx* ctx);
+int bh_setup_partitioned(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int* nbr_idx);
+int bh_partition(const bh_ctx* ctx, int64_t* row0, int64_t* nrows, int64_t* slice);
+
 /* ---- benchmark helpers (device-resident, used by bench.py) --------------------------------------- */
 /* Fill x_dev[D] with Spectra's LCG(seed 0) uniform(-0.5,0.5) sequence (Util/SimpleRandom.h:30-64), LEX order. */
 int bh_lcg_fill_dev(bh_ctx* ctx, double* x_dev, int64_t count);

@@ -1,0 +1,28 @@
+"""GPU (needs >= 2 devices; skipped otherwise): the row-partitioned eigensolve over NCCL equals the single-GPU one."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ngpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("args", [["-m", "10", "-n", "10", "-U", "4", "--nev", "20", "--point"],
+                                  ["-m", "12", "-n", "12", "-U", "1", "--nev", "2", "--ncv", "12"]])
+def test_partitioned_equals_single(args):
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(ROOT, "tools", "eigs_mgpu.py"), "--check"] + args
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, (p.stdout[-2000:], p.stderr[-2000:])
+    out = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["check"] == "ok" and out["world"] == 2
