@@ -88,6 +88,11 @@ struct bh_ctx {
     int* d_perm_tag = nullptr;
     int* d_inv_tag = nullptr;
 
+    int cheb_degree = 8;   // Chebyshev filter degree of the accelerated solver (1 = plain Lanczos; env BH_CHEB_DEGREE)
+    int cheb_pre = 3;      // plain restart cycles run first to locate the wanted end of the spectrum (env BH_CHEB_PRE)
+    double cheb_margin = 0.05;  // cut >= theta_{nev-1} + margin * (theta_{nev-1} - theta_0)   (env BH_CHEB_MARGIN)
+    double cheb_frac = 0.08;    // cut >= theta_0 + frac * (hi - theta_0)                       (env BH_CHEB_FRAC)
+    double* d_cheb[3] = {nullptr, nullptr, nullptr};
     int coop = 1;          // single cooperative launch per Lanczos step when the residual fits in registers (env BH_COOP)
     int reorth_block = 8;  // basis columns per re-orthogonalisation block (env BH_REORTH_BLOCK)
     bool reorth_block_forced = false;
@@ -139,8 +144,16 @@ int bh_build_hamiltonian(bh_ctx* ctx);    // K2: pattern, J values
 int bh_ensure_orderings(bh_ctx* ctx);     // tags, radix sort, permutations
 int bh_materialise_H(bh_ctx* ctx, double cJ, double cU, double cmu);
 int bh_materialise_sell(bh_ctx* ctx, double cJ, double cU, double cmu);  // builds the SELL copy on first use
+// y = s1 * (H x) + s2 * x + s3 * z   (the epilogue is fused into the H.v kernels; plain H.v = {1, 0, 0, NULL})
+struct BhEpilogue {
+    double s1 = 1.0, s2 = 0.0, s3 = 0.0;
+    const double* z = nullptr;
+};
 int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x_dev, double* y_dev,
-                 double xscale_unused = 1.0);
+                 const BhEpilogue& ep = BhEpilogue());
+// rigorous (Gershgorin) bounds of the spectrum of H(cJ, cU, cmu); model contexts only
+int bh_spectrum_bounds(bh_ctx* ctx, double cJ, double cU, double cmu, double* lo, double* hi);
+int bh_dist_allreduce_max(bh_ctx* ctx, double* buf_dev, int64_t count);
 int bh_ensure_workspace(bh_ctx* ctx, int ncv);
 int bh_ensure_staging(bh_ctx* ctx);
 // permute between LEX (device) and `order`: dst[pos] = src[lex(pos)] (to_order) or dst[lex(pos)] = src[pos]

@@ -61,6 +61,10 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
     if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
     if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
+    if (const char* v = getenv("BH_CHEB_DEGREE")) ctx->cheb_degree = std::max(1, atoi(v));
+    if (const char* v = getenv("BH_CHEB_PRE")) ctx->cheb_pre = std::max(1, atoi(v));
+    if (const char* v = getenv("BH_CHEB_MARGIN")) ctx->cheb_margin = atof(v);
+    if (const char* v = getenv("BH_CHEB_FRAC")) ctx->cheb_frac = atof(v);
     if (const char* v = getenv("BH_REORTH_BLOCK")) { ctx->reorth_block = std::min(BH_MAX_NCV, std::max(1, atoi(v))); ctx->reorth_block_forced = true; }
     if (const char* v = getenv("BH_HV_STAGES")) ctx->hv_stages = std::min(4, std::max(2, atoi(v)));
     *out = ctx;
@@ -101,6 +105,7 @@ int bh_release_system(bh_ctx* ctx)
     free_dev(ctx->d_part); ctx->d_part = nullptr;
     free_dev(ctx->d_counter); ctx->d_counter = nullptr;
     free_dev(ctx->d_small); ctx->d_small = nullptr;
+    for (int q = 0; q < 3; ++q) { free_dev(ctx->d_cheb[q]); ctx->d_cheb[q] = nullptr; }
     free_dev(ctx->d_x); ctx->d_x = nullptr;
     free_dev(ctx->d_y); ctx->d_y = nullptr;
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -94,6 +94,13 @@ int bh_dist_allreduce_sum(bh_ctx* ctx, double* buf, int64_t count)
     return BH_OK;
 }
 
+int bh_dist_allreduce_max(bh_ctx* ctx, double* buf, int64_t count)
+{
+    if (ctx->world < 2) return BH_OK;
+    BH_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, ncclDouble, ncclMax, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));
+    return BH_OK;
+}
+
 int bh_dist_allgather(bh_ctx* ctx, const double* send, double* recv, int64_t count_per_rank)
 {
     if (ctx->world < 2) {

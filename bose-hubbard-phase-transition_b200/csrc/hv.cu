@@ -205,7 +205,7 @@ __global__ void k_tile_cap(int64_t D, const int* __restrict__ rowptr, int* __res
 #define SELL_BATCH 8
 __global__ void __launch_bounds__(256)
 k_hv_sell(int64_t D, int64_t nslices, const int* __restrict__ sptr, const int* __restrict__ scol,
-          const double* __restrict__ sval, const double* __restrict__ x, double* __restrict__ y)
+          const double* __restrict__ sval, const double* __restrict__ x, double* __restrict__ y, BhEpilogue ep)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -227,7 +227,12 @@ k_hv_sell(int64_t D, int64_t nslices, const int* __restrict__ sptr, const int* _
             for (int u = 0; u < SELL_BATCH; ++u) acc = fma(v[u], xv[u], acc);
         }
         const int64_t r = (s << 5) + lane;
-        if (r < D) y[r] = acc;
+        if (r < D) {
+            double out = ep.s1 * acc;
+            if (ep.s2 != 0.0) out = fma(ep.s2, x[r], out);
+            if (ep.z) out = fma(ep.s3, ep.z[r], out);
+            y[r] = out;
+        }
     }
 }
 
@@ -268,7 +273,7 @@ k_hv_free(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint
 }
 
 typedef void (*hv_free_fn_t)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double, double, double,
-                             const double*, double*);
+                             const double*, double*, BhEpilogue);
 
 // K4, bond-list variant: the per-thread rank prefixes live in shared memory ([site][thread], conflict-free),
 // so the hop loop runs over the lattice's actual bond list (uniform across the block) instead of all site
@@ -277,7 +282,7 @@ typedef void (*hv_free_fn_t)(const BhTables*, int64_t, int64_t, const uint64_t*,
 __global__ void __launch_bounds__(HVF_THREADS)
 k_hv_free_bonds(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
                 const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
-                double* __restrict__ y)
+                double* __restrict__ y, BhEpilogue ep)
 {
     __shared__ BhTables t;
     __shared__ int sdn[BH_MAX_SITES][HVF_THREADS];
@@ -311,7 +316,11 @@ k_hv_free_bonds(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, cons
             acc = fma((double)w * t.sq[(bh_occ(s, dst) + 1) * ns], xv, acc);
         }
         const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
-        y[l] = diag * x[k] - cJ * acc;
+        const double xk = x[k];
+        double out = ep.s1 * (diag * xk - cJ * acc);
+        if (ep.s2 != 0.0) out = fma(ep.s2, xk, out);
+        if (ep.z) out = fma(ep.s3, ep.z[l], out);
+        y[l] = out;
     }
 }
 
@@ -323,7 +332,7 @@ template <int M, bool CLOSED>
 __global__ void __launch_bounds__(256)
 k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
                 const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
-                double* __restrict__ y)
+                double* __restrict__ y, BhEpilogue ep)
 {
     __shared__ BhTables t;
     bh_stage_tables(&t, gtab);
@@ -358,7 +367,11 @@ k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, cons
             acc = fma(t.sq[(nl + 1) * n0], xb, acc);
         }
         const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
-        y[l] = diag * x[k] - (2.0 * cJ) * acc;
+        const double xv = x[k];
+        double out = ep.s1 * (diag * xv - (2.0 * cJ) * acc);
+        if (ep.s2 != 0.0) out = fma(ep.s2, xv, out);
+        if (ep.z) out = fma(ep.s3, ep.z[l], out);
+        y[l] = out;
     }
 }
 
@@ -410,8 +423,85 @@ static hv_free_fn hv_free_kernel(int m)
     return nullptr;
 }
 
-int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x, double* y, double)
+// Gershgorin bounds of the spectrum: row k gives diag_k -/+ |cJ| sum_hops w sqrt((n_dst+1) n_src).  Used to scale
+// the Chebyshev filter of the accelerated solver (the upper bound must be rigorous: the filter explodes above it).
+__global__ void __launch_bounds__(256)
+k_gersh(const BhTables* __restrict__ gtab, int64_t nloc, const uint64_t* __restrict__ states, const double* __restrict__ dU,
+        double cJ, double cU, double cmu, double* __restrict__ part /* [2][gridDim.x] */)
 {
+    __shared__ BhTables t;
+    __shared__ double shi[8], slo[8];
+    bh_stage_tables(&t, gtab);
+    double hi = -1e300, lo = 1e300;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < nloc; l += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = states[l];
+        double off = 0.0;
+        for (int b = 0; b < t.nbonds; ++b) {
+            const int bd = t.bond[b];
+            const int dst = bd & 15, src = (bd >> 4) & 15, w = bd >> 8;
+            off += (double)w * t.sq[(bh_occ(s, dst) + 1) * bh_occ(s, src)];
+        }
+        off *= fabs(cJ);
+        const double diag = dU[l] * cU - (double)t.n * cmu;
+        hi = fmax(hi, diag + off);
+        lo = fmin(lo, diag - off);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    }
+    if ((threadIdx.x & 31) == 0) { shi[threadIdx.x >> 5] = hi; slo[threadIdx.x >> 5] = lo; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) { hi = fmax(hi, shi[q]); lo = fmin(lo, slo[q]); }
+        part[blockIdx.x] = hi;
+        part[gridDim.x + blockIdx.x] = -lo;  // stored negated so that one max-reduction serves both
+    }
+}
+
+__global__ void k_gersh_final(int nb, const double* __restrict__ part, double* __restrict__ out2)
+{
+    double a = -1e300, b = -1e300;
+    for (int i = threadIdx.x; i < nb; i += 32) { a = fmax(a, part[i]); b = fmax(b, part[nb + i]); }
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (threadIdx.x == 0) { out2[0] = a; out2[1] = b; }
+}
+
+int bh_spectrum_bounds(bh_ctx* ctx, double cJ, double cU, double cmu, double* lo, double* hi)
+{
+    if (ctx->user_matrix) return bh_fail(ctx, BH_ERR_STATE, "spectrum bounds need a model context");
+    BH_TRY(bh_ensure_workspace(ctx, 0));
+    const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(ctx->nloc, 256), (int64_t)ctx->sm_count * 4));
+    double* part = ctx->d_part;
+    k_gersh<<<nb, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, part);
+    k_gersh_final<<<1, 32, 0, ctx->stream>>>(nb, part, part + 2 * (size_t)nb);
+    ctx->launches += 2;
+    BH_TRY(bh_dist_allreduce_max(ctx, part + 2 * (size_t)nb, 2));
+    double h2[2];
+    BH_D2H(ctx, h2, part + 2 * (size_t)nb, sizeof(double) * 2);
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *hi = h2[0];
+    *lo = -h2[1];
+    return BH_OK;
+}
+
+// generic epilogue for the kernels that do not fuse it: y = s1*y + s2*x + s3*z
+__global__ void k_epilogue(int64_t n, double* __restrict__ y, const double* __restrict__ x, BhEpilogue ep)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        double out = ep.s1 * y[r] + ep.s2 * x[r];
+        if (ep.z) out = fma(ep.s3, ep.z[r], out);
+        y[r] = out;
+    }
+}
+
+int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x, double* y, const BhEpilogue& ep)
+{
+    bool fused = false;
+    const bool plain = (ep.s1 == 1.0 && ep.s2 == 0.0 && ep.z == nullptr);
     const int64_t D = ctx->D;
     if (ctx->partitioned && kernel != BH_HV_MATRIX_FREE)
         return bh_fail(ctx, BH_ERR_STATE, "a row-partitioned context has no stored matrix: use BH_HV_MATRIX_FREE");
@@ -421,7 +511,8 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, cons
         if (kernel == BH_HV_STORED) BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu));
         const int64_t ns = ctx->sell_nslices;
         const int grid = (int)std::min<int64_t>((ns + 7) / 8, (int64_t)ctx->sm_count * 8);
-        k_hv_sell<<<grid, 256, 0, ctx->stream>>>(D, ns, ctx->d_sell_ptr, ctx->d_sell_col, ctx->d_sell_valH, x, y);
+        k_hv_sell<<<grid, 256, 0, ctx->stream>>>(D, ns, ctx->d_sell_ptr, ctx->d_sell_col, ctx->d_sell_valH, x, y, ep);
+        fused = true;
         BH_LAUNCHED(ctx);
     } else if (kernel == BH_HV_STORED) {
         BH_TRY(bh_materialise_H(ctx, cJ, cU, cmu));
@@ -477,10 +568,12 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, cons
             if (ctx->free_variant == 1 && ctx->h_tab.chain) {
                 hv_free_fn_t fn = (ctx->h_tab.chain == 2) ? hv_chain_kernel<true>(ctx->m) : hv_chain_kernel<false>(ctx->m);
                 int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
-                fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y);
+                fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y, ep);
+                fused = true;
             } else if (ctx->free_variant >= 1) {
                 int grid = (int)std::min<int64_t>(nblocks(nloc, HVF_THREADS), (int64_t)ctx->sm_count * 5);
-                k_hv_free_bonds<<<grid, HVF_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y);
+                k_hv_free_bonds<<<grid, HVF_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y, ep);
+                fused = true;
             } else {
                 hv_free_fn fn = hv_free_kernel(ctx->m);
                 int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
@@ -490,6 +583,11 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, cons
         }
     } else {
         return bh_fail(ctx, BH_ERR_ARG, "unknown H.v kernel");
+    }
+    if (!fused && !plain && ctx->nloc > 0) {
+        // x here must be the LOCAL slice for the s2 term: the unfused kernels are never used on partitioned contexts
+        k_epilogue<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->nloc, y, x, ep);
+        BH_LAUNCHED(ctx);
     }
     BH_CUDA(ctx, cudaGetLastError());
     return BH_OK;

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <functional>
 #include <limits>
 
 #include "device_utils.cuh"
@@ -541,8 +542,13 @@ int bh_ensure_workspace(bh_ctx* ctx, int ncv)
     return BH_OK;
 }
 
-int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
-               BhSolve* out)
+// y = Op x on device vectors (local slices); returns a BH_* status
+typedef std::function<int(const double*, double*)> LanczosOp;
+
+// Thick-restart Lanczos for the nev algebraically smallest eigenvalues of `op`.  start_given: the start vector is
+// already in ctx->d_w (otherwise Spectra's LCG vector is used); like Spectra it is pre-multiplied by the operator.
+static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int nev, int ncv, double tol, int maxit,
+                        BhSolve* out)
 {
     const int64_t Dglobal = ctx->D, ld = ctx->ld;
     const int64_t D = ctx->nloc;  // rows held by this context (all of them unless the solve is row-partitioned)
@@ -565,8 +571,8 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
 
     BH_CUDA(ctx, cudaMemsetAsync(scal, 0, sizeof(double) * S_TOTAL, st));
     // v0 = LCG ; f = A v0 ; beta[0] = |f|   (Arnoldi.h:147-154)
-    BH_TRY(bh_lcg_fill_dev(ctx, ctx->d_w, D));
-    BH_TRY(bh_launch_hv(ctx, cJ, cU, cmu, kernel, ctx->d_w, ctx->d_f));
+    if (!start_given) BH_TRY(bh_lcg_fill_dev(ctx, ctx->d_w, D));
+    BH_TRY(op(ctx->d_w, ctx->d_f));
     if (dist) {
         k_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, scal, S_FLAG + 3, part, counter, 1);
         BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_FLAG + 3, 1));
@@ -618,7 +624,7 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
                 k_scale<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, vi, scal, i, near0);
                 BH_LAUNCHED(ctx);
             }
-            BH_TRY(bh_launch_hv(ctx, cJ, cU, cmu, kernel, vi, ctx->d_w));
+            BH_TRY(op(vi, ctx->d_w));
             ++nmatvec;
             const int subtract = (i > 0 && !first_after_restart) ? 1 : 0;
             if (dist) {
@@ -725,6 +731,146 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
     out->info.nreorth = nmatvec - 1;  // every step re-orthogonalises (see DESIGN.md on partial re-orthogonalisation)
     out->info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     if (nconv < nev) return bh_fail(ctx, BH_ERR_NOCONV, "Eigenvalue computation failed.");
+    return BH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Solver driver.  Plain mode (cheb_degree = 1) is the reference's algorithm step for step.  The accelerated
+// mode runs the same thick-restart Lanczos on a Chebyshev polynomial of H:
+//   stage 1  a few plain restart cycles give Ritz values theta_0 <= ... (upper bounds of the eigenvalues by
+//            interlacing), so cut = theta_{nev-1} + margin is guaranteed to lie above the nev wanted levels;
+//   stage 2  Lanczos on B = -/+T_d((H - c)/e), [cut, hi] -> [-1, 1] with hi the Gershgorin bound: the wanted end
+//            is amplified like cosh(d acosh(.)) and every Lanczos step (one re-orthogonalisation against the
+//            basis, the dominant cost) advances the Krylov polynomial by d degrees.  The d applications of H use
+//            the fused epilogue of the H.v kernels (no extra vector passes);
+//   stage 3  Rayleigh-Ritz of H itself on the final basis (ncv H.v + ncv multi-dots, host 41 x 41 eigenproblem):
+//            eigenvalues and vectors of H, not of the polynomial.
+// Measured (numpy model, m=n=8): d = 7 needs 4.5x fewer Lanczos steps for 1.4-1.6x more H.v; eigenvalues agree
+// with the plain solver to 1e-12.
+// ---------------------------------------------------------------------------------------------------------
+int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
+               BhSolve* out)
+{
+    const auto t_start = std::chrono::steady_clock::now();
+    int hv_count = 0;
+    LanczosOp plain = [&](const double* x, double* y) {
+        ++hv_count;
+        return bh_launch_hv(ctx, cJ, cU, cmu, kernel, x, y);
+    };
+    const int d = ctx->cheb_degree;
+    const bool accel = d > 1 && !ctx->user_matrix && kernel != BH_HV_USER && ctx->D >= 2000 && ncv >= nev + 2 && ncv <= ctx->D;
+    if (!accel) {
+        const int rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
+        out->info.nmatvec = hv_count;
+        return rc;
+    }
+    // ---- stage 1 ----
+    BhSolve s1;
+    int rc = lanczos_core(ctx, plain, false, nev, ncv, tol, std::min(maxit, ctx->cheb_pre), &s1);
+    if (rc != BH_ERR_NOCONV || (int)s1.evals.size() < nev) {  // converged already, or a real error
+        *out = s1;
+        out->info.nmatvec = hv_count;
+        return rc;
+    }
+    double lo = 0, hi = 0;
+    BH_TRY(bh_spectrum_bounds(ctx, cJ, cU, cmu, &lo, &hi));
+    const double th0 = s1.evals[0], thn = s1.evals[nev - 1];
+    hi += 1e-9 * (hi - lo) + 1e-12;
+    double cut = std::max(thn + ctx->cheb_margin * (thn - th0), th0 + ctx->cheb_frac * (hi - th0));
+    if (!(cut < th0 + 0.8 * (hi - th0))) {  // no room for a filter: finish with the plain solver
+        rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
+        out->info.nmatvec = hv_count;
+        return rc;
+    }
+    const double c = 0.5 * (hi + cut), e = 0.5 * (hi - cut);
+    // start vector of stage 2: the sum of the stage-1 Ritz vectors of the wanted end
+    {
+        std::vector<double> ysum(ncv, 0.0);
+        for (int l = 0; l < nev; ++l)
+            for (int r = 0; r < ncv; ++r) ysum[r] += s1.Y[r + (size_t)l * ncv];
+        BH_H2D(ctx, ctx->d_small, ysum.data(), sizeof(double) * ncv);
+        const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(ctx->nloc, VEC_THREADS), (int64_t)ctx->sm_count * 4));
+        k_lincomb<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->nloc, ctx->ld, ctx->d_V, ncv, ctx->d_small, ctx->d_w);
+        BH_LAUNCHED(ctx);
+    }
+    for (int q = 0; q < 3; ++q)
+        if (!ctx->d_cheb[q]) {
+            BH_CUDA(ctx, cudaMalloc(&ctx->d_cheb[q], sizeof(double) * ctx->ld));
+            BH_CUDA(ctx, cudaMemsetAsync(ctx->d_cheb[q], 0, sizeof(double) * ctx->ld, ctx->stream));
+        }
+    // ---- stage 2 ----
+    LanczosOp cheb = [&](const double* x, double* y) {
+        const double* tkm2 = x;        // T_{k-2}
+        const double* tkm1 = nullptr;  // T_{k-1}
+        for (int k = 1; k <= d; ++k) {
+            BhEpilogue ep;
+            if (k == 1) {
+                ep.s1 = 1.0 / e; ep.s2 = -c / e;
+            } else {
+                ep.s1 = 2.0 / e; ep.s2 = -2.0 * c / e; ep.s3 = -1.0; ep.z = tkm2;
+            }
+            const bool last = (k == d);
+            if (last && (d % 2 == 0)) {  // even degree: T_d > 0 at the wanted end -> flip so that it becomes the lowest
+                ep.s1 = -ep.s1; ep.s2 = -ep.s2; ep.s3 = -ep.s3;
+            }
+            double* dst = last ? y : ctx->d_cheb[k % 3];
+            const double* src = (k == 1) ? x : tkm1;
+            ++hv_count;
+            BH_TRY(bh_launch_hv(ctx, cJ, cU, cmu, kernel, src, dst, ep));
+            if (k >= 2) tkm2 = tkm1;
+            tkm1 = dst;
+        }
+        return (int)BH_OK;
+    };
+    BhSolve s2;
+    rc = lanczos_core(ctx, cheb, true, nev, ncv, tol, maxit, &s2);
+    const int restarts = s1.info.nrestart + s2.info.nrestart;
+    if (rc != BH_OK) {
+        *out = s2;
+        out->info.nmatvec = hv_count;
+        out->info.nrestart = restarts;
+        return rc;
+    }
+    // ---- stage 3: Rayleigh-Ritz of H on span(V) ----
+    {
+        const int64_t n = ctx->nloc, ld = ctx->ld;
+        const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(n, VEC_THREADS), (int64_t)ctx->sm_count * 4));
+        const bool dist = ctx->partitioned && ctx->world > 1;
+        for (int col = 0; col < ncv; ++col) {
+            BH_TRY(plain(ctx->d_V + (int64_t)col * ld, ctx->d_w));
+            k_gemv_t<true><<<G, VEC_THREADS, 0, ctx->stream>>>(n, ld, ctx->d_V, 0, ncv, ctx->d_w, ctx->d_scal, 0, 0, ctx->d_part,
+                                                              ctx->d_counter, 1);
+            BH_LAUNCHED(ctx);
+            if (dist) BH_TRY(bh_dist_allreduce_sum(ctx, ctx->d_scal + S_VF, ncv));
+            BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_small + (size_t)col * ncv, ctx->d_scal + S_VF, sizeof(double) * ncv,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        std::vector<double> M((size_t)ncv * ncv), evH, Z;
+        BH_D2H(ctx, M.data(), ctx->d_small, sizeof(double) * (size_t)ncv * ncv);
+        BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int a = 0; a < ncv; ++a)
+            for (int b = a + 1; b < ncv; ++b) {
+                const double v = 0.5 * (M[a + (size_t)b * ncv] + M[b + (size_t)a * ncv]);
+                M[a + (size_t)b * ncv] = M[b + (size_t)a * ncv] = v;
+            }
+        bh_sym_eig(ncv, M, evH, Z);
+        if (!(evH[nev - 1] < cut)) {
+            // the wanted levels were not all below the cut (cannot happen by interlacing; kept as a safety net)
+            rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
+            out->info.nmatvec = hv_count;
+            return rc;
+        }
+        out->nev = nev;
+        out->ncv = ncv;
+        out->evals.assign(evH.begin(), evH.begin() + nev);
+        out->Y.assign(Z.begin(), Z.begin() + (size_t)ncv * nev);
+    }
+    out->info = s2.info;
+    out->info.nconv = nev;
+    out->info.nmatvec = hv_count;
+    out->info.nrestart = restarts;
+    out->info.nreorth = s1.info.nreorth + s2.info.nreorth;
+    out->info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     return BH_OK;
 }
 

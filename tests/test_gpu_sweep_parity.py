@@ -1,0 +1,50 @@
+"""GPU: the default (Chebyshev-accelerated) solver against the oracle's Spectra-style solver across the range of
+the sweep -- all 20 levels as a multiset (degenerate pairs included), the three phase.txt columns, and the plain
+solver (BH_CHEB_DEGREE=1) as a second witness."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def m8():
+    m = n = 8
+    t, b = O.basis(m, n)
+    jc = O.hopping_csc(m, O.chain(m), t, b)
+    dU, dN = O.diagonals(m, b)
+    return m, t, b, jc, dU, dN
+
+
+@pytest.mark.parametrize("U,mu", [(0.5, 0.0), (1.0, 3.0), (2.0, 0.0), (8.0, 1.0), (16.0, 5.0), (32.0, 31.0)])
+def test_points_across_the_sweep(pkg, ctx_factory, m8, U, mu):
+    m, t, b, jc, dU, dN = m8
+    ctx = ctx_factory(m, m)
+    ref = O.point(m, t, b, jc, dU, dN, 1.0, U, mu)
+    for kernel in (pkg.capi.HV_STORED, pkg.capi.HV_MATRIX_FREE):
+        got = ctx.point(1.0, U, mu, kernel=kernel)
+        scale = np.maximum(np.abs(ref["evals"]), np.abs(ref["evals"][0]))
+        assert np.all(np.abs(got["evals"] - ref["evals"]) <= 1e-10 * scale), (kernel, got["evals"] - ref["evals"])
+        assert np.allclose(got["out3"], ref["out3"], rtol=1e-9, atol=1e-12)
+        assert np.abs(got["rho"] - ref["rho"]).max() <= 1e-10 * np.abs(ref["rho"]).max()
+
+
+def test_plain_and_accelerated_solvers_agree(pkg):
+    m = n = 10
+    res = {}
+    for deg in ("1", "8", "5"):
+        os.environ["BH_CHEB_DEGREE"] = deg
+        try:
+            c = pkg.Context(0).setup(m, n)
+            res[deg] = c.eigs(1.0, 6.0, 2.0, nev=20, kernel=pkg.capi.HV_MATRIX_FREE)
+            c.close()
+        finally:
+            del os.environ["BH_CHEB_DEGREE"]
+    base = res["1"]["evals"]
+    for deg in ("8", "5"):
+        assert np.all(np.abs(res[deg]["evals"] - base) <= 1e-10 * np.maximum(np.abs(base), abs(base[0])))
+        assert res[deg]["nrestart"] < res["1"]["nrestart"]
