@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbh_b200.so")
+LIB_PATH = os.environ.get("BH_B200_LIB", os.path.join(HERE, "libbh_b200.so"))  # override: kernel-variant experiments
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOCONV, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 LEX, TAG_SORTED, REF_SCATTER = 0, 1, 2

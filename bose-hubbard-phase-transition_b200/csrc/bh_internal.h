@@ -19,6 +19,9 @@ struct BhTables {
     // f[q][R] = [R > 0] * C(R - 1 + m - 1 - q, m - 1 - q): number of basis states that precede, on site q,
     // a state with R bosons on the sites after q (descending-lexicographic rank = sum_q f[q][R_q]).
     int f[BH_MAX_SITES][BH_MAX_BOSONS + 3];
+    // rank change of a nearest-neighbour hop across bond (q, q+1) when R bosons sit beyond site q:
+    // gh[q][R].x = f[q][R-1] - f[q][R] (boson moves q+1 -> q), .y = f[q][R+1] - f[q][R] (boson moves q -> q+1)
+    int2 gh[BH_MAX_SITES][BH_MAX_BOSONS + 3];
     // w[dst][src]: how many times the ordered bond appears in the neighbour list, both directions summed
     // (the reference pushes (index,k) and (k,index) for every listed neighbour, src/hamiltonian.cpp:184-185).
     unsigned char w[BH_MAX_SITES][BH_MAX_SITES];

@@ -294,6 +294,11 @@ int bh_build_basis(bh_ctx* ctx)
     t.n = n;
     for (int q = 0; q < m - 1; ++q)
         for (int R = 0; R <= n + 1; ++R) t.f[q][R] = (R > 0) ? (int)binom64(R - 1 + m - 1 - q, m - 1 - q) : 0;
+    for (int q = 0; q < m - 1; ++q)
+        for (int R = 0; R <= n; ++R) {
+            t.gh[q][R].x = (R >= 1 ? t.f[q][R - 1] : t.f[q][R]) - t.f[q][R];
+            t.gh[q][R].y = t.f[q][R + 1] - t.f[q][R];
+        }
     for (int a = 0; a < 256; ++a) t.sq[a] = std::sqrt((double)a);
     for (int i = 0; i < m; ++i) t.logp[i] = std::log(kPrimes[i]);
     int nb = 0;

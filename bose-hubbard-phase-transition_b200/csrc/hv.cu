@@ -328,8 +328,11 @@ k_hv_free_bonds(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, cons
 // a nearest-neighbour hop across bond (q, q+1) changes the rank by ONE table difference that depends on
 // (q, R_q) only, so the row is produced in a single sweep over the sites with no prefix arrays; the periodic
 // bond uses the accumulated totals.  ~3x fewer instructions per row than the bond-list kernel.
+#ifndef CHAIN_MIN_BLOCKS
+#define CHAIN_MIN_BLOCKS 4
+#endif
 template <int M, bool CLOSED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CHAIN_MIN_BLOCKS)
 k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
                 const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
                 double* __restrict__ y, BhEpilogue ep)
@@ -340,29 +343,27 @@ k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, cons
     for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = row0 + l;
         const uint64_t s = states[l];
-        const double* xk = x + k;
+        const int kk = (int)k;
         const int n0 = bh_occ(s, 0);
         int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
         double acc = 0.0;
 #pragma unroll
         for (int q = 0; q < M - 1; ++q) {
             const int nnext = bh_occ(s, q + 1);
-            const int f0 = t.f[q][R];
-            const int g = (R >= 1 ? t.f[q][R - 1] : f0) - f0;  // boson moves q+1 -> q
-            const int h = t.f[q][R + 1] - f0;                   // boson moves q -> q+1
-            const double xa = nnext ? __ldg(xk + g) : 0.0;
-            const double xb = nprev ? __ldg(xk + h) : 0.0;
+            const int2 gh = t.gh[q][R];  // .x: boson moves q+1 -> q, .y: q -> q+1
+            const double xa = nnext ? __ldg(x + (kk + gh.x)) : 0.0;
+            const double xb = nprev ? __ldg(x + (kk + gh.y)) : 0.0;
             acc = fma(t.sq[(nprev + 1) * nnext], xa, acc);
             acc = fma(t.sq[(nnext + 1) * nprev], xb, acc);
-            tdn += g;
-            tup += h;
+            tdn += gh.x;
+            tup += gh.y;
             R -= nnext;
             nprev = nnext;
         }
         if (CLOSED) {
             const int nl = nprev;  // occupation of the last site
-            const double xa = nl ? __ldg(xk + tdn) : 0.0;  // M-1 -> 0
-            const double xb = n0 ? __ldg(xk + tup) : 0.0;  // 0 -> M-1
+            const double xa = nl ? __ldg(x + (kk + tdn)) : 0.0;  // M-1 -> 0
+            const double xb = n0 ? __ldg(x + (kk + tup)) : 0.0;  // 0 -> M-1
             acc = fma(t.sq[(n0 + 1) * nl], xa, acc);
             acc = fma(t.sq[(nl + 1) * n0], xb, acc);
         }

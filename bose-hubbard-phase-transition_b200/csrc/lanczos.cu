@@ -49,6 +49,23 @@ __device__ __forceinline__ bool bh_last_block(unsigned int* counter)
     return is_last;
 }
 
+// LCG(16807) sequence starting at element `first` of the global stream (fresh vectors after a breakdown)
+__global__ void k_lcg_seq(int64_t first, int64_t n, double* __restrict__ out)
+{
+    const unsigned long long M = 2147483647ull;
+    const int64_t start = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 64;
+    if (start >= n) return;
+    unsigned long long seed = 1, base = 16807ull;
+    for (unsigned long long p = (unsigned long long)(first + start); p; p >>= 1) {
+        if (p & 1) seed = seed * base % M;
+        base = base * base % M;
+    }
+    for (int64_t i = start; i < min(start + 64, n); ++i) {
+        seed = seed * 16807ull % M;
+        out[i] = (double)(long long)seed / 2147483647.0 - 0.5;
+    }
+}
+
 // |v| -> scal[dst]  (used once for |A v0|)
 __global__ void __launch_bounds__(VEC_THREADS)
 k_norm(int64_t D, const double* __restrict__ v, double* __restrict__ scal, int dst, double* __restrict__ part,
@@ -76,8 +93,10 @@ k_scale(int64_t D, const double* __restrict__ f, double* __restrict__ vi, double
     double inv = 0.0;
     if (beta > thresh)
         inv = 1.0 / beta;
-    else if (blockIdx.x == 0 && threadIdx.x == 0)
-        scal[S_FLAG] = 1.0;
+    else if (blockIdx.x == 0 && threadIdx.x == 0 && scal[S_FLAG] == 0.0) {
+        scal[S_FLAG] = 1.0;          // breakdown: the Krylov space became invariant ...
+        scal[S_FLAG + 1] = (double)i;  // ... before basis column i could be formed
+    }
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < D; r += (int64_t)gridDim.x * blockDim.x)
         vi[r] = f[r] * inv;
 }
@@ -455,7 +474,10 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
         scal[S_ALPHA + i] = alpha;
         scal[S_OFFD + i] = offd;
         scal[S_BETA + i + 1] = beta;
-        if (!(beta > thresh)) scal[S_FLAG] = 1.0;
+        if (!(beta > thresh) && scal[S_FLAG] == 0.0) {
+            scal[S_FLAG] = 1.0;
+            scal[S_FLAG + 1] = (double)(i + 1);
+        }
     }
 }
 
@@ -615,12 +637,16 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
         }
     }
 
+    // steps that start from a fresh random vector after a breakdown (Spectra's expand_basis, Arnoldi.h:64-113):
+    // no coupling to the previous column, re-orthogonalised twice
+    std::vector<char> fresh(ncv + 2, 0);
+    int istart = 0, nfresh = 0;
     for (;;) {
-        for (int i = from; i < ncv; ++i) {
+        for (int i = istart; i < ncv; ++i) {
             double* vi = V + (int64_t)i * ld;
-            const bool first_after_restart = (from > 0 && i == from);
+            const bool first_after_restart = (from > 0 && i == from) || fresh[i];
             // v_i = f / beta: written by the previous cooperative step except at the start of a cycle
-            if (!coop_grid || i == from) {
+            if (!coop_grid || i == istart) {
                 k_scale<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, vi, scal, i, near0);
                 BH_LAUNCHED(ctx);
             }
@@ -675,8 +701,37 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
         BH_CUDA(ctx, cudaGetLastError());
         BH_D2H(ctx, h_scal.data(), scal, sizeof(double) * S_TOTAL);
         BH_CUDA(ctx, cudaStreamSynchronize(st));
-        if (h_scal[S_FLAG] != 0.0)
-            return bh_fail(ctx, BH_ERR_NOCONV, "Lanczos breakdown (invariant subspace reached before ncv steps)");
+        if (h_scal[S_FLAG] != 0.0) {
+            // invariant subspace before the basis was full (e.g. J = 0: H diagonal with few distinct levels).
+            // Like Spectra: continue from a new random vector orthogonal to the columns built so far.
+            const int ib = (int)h_scal[S_FLAG + 1];
+            if (++nfresh > 4 * ncv || ib < 0 || ib >= ncv)
+                return bh_fail(ctx, BH_ERR_NOCONV, "Lanczos breakdown (invariant subspace reached before ncv steps)");
+            BH_CUDA(ctx, cudaMemsetAsync(scal + S_FLAG, 0, sizeof(double) * 2, st));
+            const int64_t first = (ctx->partitioned ? ctx->row0 : 0) + (int64_t)7919 * nfresh;
+            k_lcg_seq<<<nblocks((D + 63) / 64, 128), 128, 0, st>>>(first, D, ctx->d_f);
+            BH_LAUNCHED(ctx);
+            if (ib > 0) {
+                for (int pass = 0; pass < 2; ++pass) {
+                    k_gemv_t<true><<<G, VEC_THREADS, 0, st>>>(D, ld, V, 0, ib, ctx->d_f, scal, ib - 1, 0, part, counter, 1);
+                    if (dist) BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_VF, ib));
+                    k_gemv_n_norm<true><<<G, VEC_THREADS, 0, st>>>(D, ld, V, 0, ib, ctx->d_f, scal, ib - 1, part, counter, dist ? 1 : 0);
+                    if (dist) {
+                        BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_FLAG + 3, 1));
+                        k_fin_sqrt<<<1, 1, 0, st>>>(scal, S_FLAG + 3, S_BETA + ib);
+                    }
+                }
+            } else if (dist) {
+                k_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, scal, S_FLAG + 3, part, counter, 1);
+                BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_FLAG + 3, 1));
+                k_fin_sqrt<<<1, 1, 0, st>>>(scal, S_FLAG + 3, S_BETA + 0);
+            } else {
+                k_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_f, scal, S_BETA + 0, part, counter);
+            }
+            fresh[ib] = 1;
+            istart = ib;
+            continue;
+        }
         // projected matrix: diag(theta) + coupling row at `from`, tridiagonal afterwards
         T.assign((size_t)ncv * ncv, 0.0);
         for (int l = 0; l < from; ++l) {
@@ -720,6 +775,8 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
         // the residual f and its norm carry over: V_knew = f / beta_last
         BH_CUDA(ctx, cudaMemcpyAsync(scal + S_BETA + knew, scal + S_BETA + ncv, sizeof(double), cudaMemcpyDeviceToDevice, st));
         from = knew;
+        istart = from;
+        std::fill(fresh.begin(), fresh.end(), 0);
     }
     out->nev = nev;
     out->ncv = ncv;
