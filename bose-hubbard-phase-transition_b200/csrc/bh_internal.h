@@ -96,6 +96,7 @@ struct bh_ctx {
     double cheb_margin = 0.05;  // cut >= theta_{nev-1} + margin * (theta_{nev-1} - theta_0)   (env BH_CHEB_MARGIN)
     double cheb_frac = 0.08;    // cut >= theta_0 + frac * (hi - theta_0)                       (env BH_CHEB_FRAC)
     double* d_cheb[3] = {nullptr, nullptr, nullptr};
+    int compress_tiled = 1;  // register-tiled restart GEMM (env BH_COMPRESS_TILED)
     int coop = 1;          // single cooperative launch per Lanczos step when the residual fits in registers (env BH_COOP)
     int reorth_block = 8;  // basis columns per re-orthogonalisation block (env BH_REORTH_BLOCK)
     bool reorth_block_forced = false;

@@ -61,6 +61,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
     if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
     if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
+    if (const char* v = getenv("BH_COMPRESS_TILED")) ctx->compress_tiled = atoi(v);
     if (const char* v = getenv("BH_CHEB_DEGREE")) ctx->cheb_degree = std::max(1, atoi(v));
     if (const char* v = getenv("BH_CHEB_PRE")) ctx->cheb_pre = std::max(1, atoi(v));
     if (const char* v = getenv("BH_CHEB_MARGIN")) ctx->cheb_margin = atof(v);

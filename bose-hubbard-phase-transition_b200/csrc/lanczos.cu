@@ -535,6 +535,60 @@ k_compress(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, const 
     }
 }
 
+// K6, register-tiled: a CTA owns 128 rows (staged once in shared memory, so the update is safe in place), every
+// thread accumulates a 4 x 4 tile (4 rows x 4 output columns) -> 16 FMAs per 4 shared-memory loads instead of 1 per 2.
+#define CT_ROWS 128
+#define CT_COLS 32
+__global__ void __launch_bounds__(256)
+k_compress_tiled(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, const double* __restrict__ Y)
+{
+    extern __shared__ __align__(16) double sm2[];
+    double* vt = sm2;                           // [ncv][CT_ROWS]
+    double* yc = sm2 + (size_t)ncv * CT_ROWS;   // [ncv][CT_COLS]   (row j = coefficients of basis vector j)
+    const int64_t r0 = (int64_t)blockIdx.x * CT_ROWS;
+    const int rg = threadIdx.x & 31, cgp = threadIdx.x >> 5;  // 32 row groups x 8 column groups
+    for (int idx = threadIdx.x; idx < ncv * CT_ROWS; idx += blockDim.x) {
+        const int j = idx / CT_ROWS, r = idx % CT_ROWS;
+        vt[idx] = (r0 + r < D) ? V[(int64_t)j * ld + r0 + r] : 0.0;
+    }
+    for (int c0 = 0; c0 < k; c0 += CT_COLS) {
+        const int nck = min(CT_COLS, k - c0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < ncv * CT_COLS; idx += blockDim.x) {
+            const int j = idx / CT_COLS, c = idx % CT_COLS;
+            yc[idx] = (c < nck) ? Y[(size_t)(c0 + c) * ncv + j] : 0.0;
+        }
+        __syncthreads();
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int j = 0; j < ncv; ++j) {
+            const double2 a01 = *reinterpret_cast<const double2*>(vt + j * CT_ROWS + rg * 4);
+            const double2 a23 = *reinterpret_cast<const double2*>(vt + j * CT_ROWS + rg * 4 + 2);
+            const double2 b01 = *reinterpret_cast<const double2*>(yc + j * CT_COLS + cgp * 4);
+            const double2 b23 = *reinterpret_cast<const double2*>(yc + j * CT_COLS + cgp * 4 + 2);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+            const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+            for (int ra = 0; ra < 4; ++ra)
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) acc[ra][cb] = fma(a[ra], b[cb], acc[ra][cb]);
+        }
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const int c = cgp * 4 + cb;
+            if (c < nck) {
+                double* dst = V + (int64_t)(c0 + c) * ld + r0 + rg * 4;
+#pragma unroll
+                for (int ra = 0; ra < 4; ++ra)
+                    if (r0 + rg * 4 + ra < D) dst[ra] = acc[ra][cb];
+            }
+        }
+    }
+}
+
 int bh_ensure_workspace(bh_ctx* ctx, int ncv)
 {
     if (!ctx->D) return bh_fail(ctx, BH_ERR_STATE, "no system: call bh_setup first");
@@ -614,6 +668,9 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
     // column block of the re-orthogonalisation: L2-sized blocks for big systems, everything at once when the
     // whole basis is L2-resident anyway (then launch count is what matters)
     const int rblock = ((size_t)ld * 8 * (ncv + 1) <= ((size_t)48 << 20) && !ctx->reorth_block_forced) ? ncv + 1 : ctx->reorth_block;
+    const size_t tiled_smem = sizeof(double) * (size_t)ncv * (CT_ROWS + CT_COLS);
+    const bool tiled = tiled_smem <= 200 * 1024 && ctx->compress_tiled;
+    if (tiled) BH_CUDA(ctx, cudaFuncSetAttribute(k_compress_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
     const size_t compress_smem = sizeof(double) * ((size_t)ncv * CRsel + (size_t)CK * ncv);
     if (compress_smem > 48 * 1024) {
         if (CRsel == 64)
@@ -764,7 +821,9 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
         if (knew > ncv - 1) knew = ncv - 1;
         // K6: V[:, 0..knew) <- V Y[:, 0..knew)
         BH_H2D(ctx, ctx->d_small, Y.data(), sizeof(double) * (size_t)ncv * knew);
-        if (CRsel == 64)
+        if (tiled)
+            k_compress_tiled<<<nblocks(D, CT_ROWS), 256, tiled_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
+        else if (CRsel == 64)
             k_compress<64><<<nblocks(D, 64), 256, compress_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
         else
             k_compress<16><<<nblocks(D, 16), 256, compress_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
