@@ -109,6 +109,8 @@ struct bh_ctx {
     double* d_part = nullptr;   // per-block partial sums
     unsigned int* d_counter = nullptr;
     double* d_small = nullptr;  // small matrices uploaded from the host (Y, coefficients)
+    double* d_spdm_scratch = nullptr;  // SPDM partials + result
+    size_t spdm_scratch_bytes = 0;
     double* d_x = nullptr;      // staging vectors for host-pointer entry points
     double* d_y = nullptr;
     double* h_pinned = nullptr;  // pinned host staging

@@ -107,6 +107,8 @@ int bh_release_system(bh_ctx* ctx)
     free_dev(ctx->d_counter); ctx->d_counter = nullptr;
     free_dev(ctx->d_small); ctx->d_small = nullptr;
     for (int q = 0; q < 3; ++q) { free_dev(ctx->d_cheb[q]); ctx->d_cheb[q] = nullptr; }
+    free_dev(ctx->d_spdm_scratch); ctx->d_spdm_scratch = nullptr;
+    ctx->spdm_scratch_bytes = 0;
     free_dev(ctx->d_x); ctx->d_x = nullptr;
     free_dev(ctx->d_y); ctx->d_y = nullptr;
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -102,10 +102,16 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
     BH_TRY(bh_ensure_workspace(ctx, 0));
     const int64_t nloc = ctx->nloc;
     const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(nloc, SPDM_THREADS), (int64_t)ctx->sm_count * 2));
-    double* d_part = nullptr;
-    double* d_rho = nullptr;
-    BH_CUDA(ctx, cudaMalloc(&d_part, sizeof(double) * (size_t)gx * m * m));
-    BH_CUDA(ctx, cudaMalloc(&d_rho, sizeof(double) * m * m));
+    // scratch lives in the context (no cudaMalloc / cudaFree on the per-point path: both synchronise the device)
+    const size_t need = sizeof(double) * ((size_t)gx * m * m + (size_t)m * m);
+    if (ctx->spdm_scratch_bytes < need) {
+        if (ctx->d_spdm_scratch) cudaFree(ctx->d_spdm_scratch);
+        ctx->d_spdm_scratch = nullptr;
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_spdm_scratch, need));
+        ctx->spdm_scratch_bytes = need;
+    }
+    double* d_part = ctx->d_spdm_scratch;
+    double* d_rho = d_part + (size_t)gx * m * m;
     const bool dist = ctx->partitioned && ctx->world > 1;
     const double* phi_full = phi_dev;
     if (dist) {  // phi_dev is the local slice: exchange it once, reduce the local partial matrices afterwards
@@ -120,8 +126,6 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
     BH_CUDA(ctx, cudaGetLastError());
     BH_D2H(ctx, rho_host, d_rho, sizeof(double) * m * m);
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_part);
-    cudaFree(d_rho);
     return BH_OK;
 }
 

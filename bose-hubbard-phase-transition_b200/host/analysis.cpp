@@ -68,9 +68,14 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
         throw std::runtime_error("no CUDA device: the exact path has no CPU fallback");
     const int ngpu = (opt.gpus > 0) ? std::min(opt.gpus, ndev) : ndev;
 
-    std::vector<bh_ctx*> ctxs(ngpu, nullptr);
-    for (int d = 0; d < ngpu; ++d) {
-        if (bh_ctx_create(d, &ctxs[d]) != BH_OK) throw std::runtime_error(bh_last_error(nullptr));
+    // Optional: several grid points concurrently per GPU, each on its own context (own stream and workspace).
+    // Measured on B200 (m=n=8 and 10, 121 points): no gain -- cooperative launches of different streams serialise
+    // and the host threads contend for the driver -- so the default is one context per GPU.
+    int per_gpu = std::max(1, opt.contexts_per_gpu);
+    const int nworkers = ngpu * per_gpu;
+    std::vector<bh_ctx*> ctxs(nworkers, nullptr);
+    for (int d = 0; d < nworkers; ++d) {
+        if (bh_ctx_create(d % ngpu, &ctxs[d]) != BH_OK) throw std::runtime_error(bh_last_error(nullptr));
         if (bh_setup(ctxs[d], m, n, nbr_ptr.data(), nbr_idx.data()) != BH_OK) {
             std::string msg = bh_last_error(ctxs[d]);
             for (bh_ctx* c : ctxs) bh_ctx_destroy(c);
@@ -115,7 +120,7 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
             }
         };
         std::vector<std::thread> team;
-        for (int d = 0; d < ngpu; ++d) team.emplace_back(worker, d);
+        for (int d = 0; d < nworkers; ++d) team.emplace_back(worker, d);
         for (auto& th : team) th.join();
         if (failure) break;
 

@@ -33,6 +33,7 @@ static void print_usage()
               << "  -l, --lattice   chain (default) or LXxLY[xLZ] periodic box\n"
               << "  -k, --kernel    stored (default) or free (matrix-free H.v)\n"
               << "  -o, --output    Output file (default phase.txt)\n"
+              << "  -c, --concurrent Grid points solved concurrently per GPU (default 1)\n"
               << "      --no-plot   Do not run plot.py afterwards\n";
 }
 
@@ -44,7 +45,7 @@ int main(int argc, char* argv[])
     Analysis::ExactOptions opt;
     bool plot = true;
 
-    const char* const short_opts = "m:n:J:U:u:r:s:f:t:i:e:g:l:k:o:h";
+    const char* const short_opts = "m:n:J:U:u:r:s:f:t:i:e:g:l:k:o:c:h";
     const option long_opts[] = {{"sites", required_argument, nullptr, 'm'},      {"bosons", required_argument, nullptr, 'n'},
                                 {"hopping", required_argument, nullptr, 'J'},    {"interaction", required_argument, nullptr, 'U'},
                                 {"potential", required_argument, nullptr, 'u'},  {"range", required_argument, nullptr, 'r'},
@@ -52,7 +53,7 @@ int main(int argc, char* argv[])
                                 {"type", required_argument, nullptr, 't'},       {"iterations", required_argument, nullptr, 'i'},
                                 {"epsilon", required_argument, nullptr, 'e'},    {"gpus", required_argument, nullptr, 'g'},
                                 {"lattice", required_argument, nullptr, 'l'},    {"kernel", required_argument, nullptr, 'k'},
-                                {"output", required_argument, nullptr, 'o'},     {"no-plot", no_argument, nullptr, 1000},
+                                {"output", required_argument, nullptr, 'o'},     {"concurrent", required_argument, nullptr, 'c'},     {"no-plot", no_argument, nullptr, 1000},
                                 {"help", no_argument, nullptr, 'h'},             {nullptr, no_argument, nullptr, 0}};
     while (true) {
         const int o = getopt_long(argc, argv, short_opts, long_opts, nullptr);
@@ -80,6 +81,7 @@ int main(int argc, char* argv[])
             }
             case 'k': opt.kernel = (std::string(optarg) == "free") ? 1 : 0; break;
             case 'o': opt.output = optarg; break;
+            case 'c': opt.contexts_per_gpu = std::stoi(optarg); break;
             case 1000: plot = false; break;
             case 'h':
             default: print_usage(); return 0;
