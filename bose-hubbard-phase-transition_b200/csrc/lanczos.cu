@@ -941,6 +941,12 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
     BhSolve s2;
     rc = lanczos_core(ctx, cheb, true, nev, ncv, tol, maxit, &s2);
     const int restarts = s1.info.nrestart + s2.info.nrestart;
+    if (rc == BH_ERR_NOCONV) {  // the filtered iteration stalled: fall back to the reference algorithm
+        rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
+        out->info.nmatvec = hv_count;
+        out->info.nrestart += restarts;
+        return rc;
+    }
     if (rc != BH_OK) {
         *out = s2;
         out->info.nmatvec = hv_count;
