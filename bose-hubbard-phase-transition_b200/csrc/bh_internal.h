@@ -66,6 +66,8 @@ struct bh_ctx {
     // SELL-32 copy of the stored H (variant 2): slices of 32 consecutive rows, column-major inside a slice,
     // padded to the longest row of the slice (padding = zero value pointing at the row's own column)
     int64_t sell_nslices = 0, sell_entries = 0;
+    int sell_sigma = 256;           // sorting window (rows), multiple of 32 (env BH_SELL_SIGMA; 32 = plain SELL-32)
+    int* d_sell_row = nullptr;      // [nslices * 32] slot -> row (-1 = padding slot)
     int* d_sell_ptr = nullptr;      // [nslices + 1] entry offset of each slice
     int* d_sell_col = nullptr;
     double* d_sell_valJ = nullptr;

@@ -265,37 +265,59 @@ int bh_materialise_H(bh_ctx* ctx, double cJ, double cU, double cmu)
 // j-th entries of the 32 rows of a slice are mostly the same hop applied to neighbouring states and the
 // gathers of x fall into a few cache lines).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_sell_sizes(int64_t D, int64_t nslices, const int* __restrict__ rowptr, int* __restrict__ sizes)
+// sigma-sorting: inside every window of SIGMA consecutive rows the rows are ordered by decreasing length (stable),
+// so that the 32 rows of a slice have nearly equal lengths (padding 16.8 % -> 6.0 % at sigma = 128 on the m=n=12
+// chain) while staying close enough in LEX order for the x gathers to share cache lines.  slot -> row map, -1 = none.
+__global__ void k_sell_perm(int64_t D, int sigma, const int* __restrict__ rowptr, int* __restrict__ slot_row)
+{
+    extern __shared__ int slen[];
+    const int64_t row = (int64_t)blockIdx.x * sigma + threadIdx.x;
+    const int len = (row < D) ? rowptr[row + 1] - rowptr[row] : -1;
+    slen[threadIdx.x] = len;
+    __syncthreads();
+    int rank = 0;
+    for (int j = 0; j < sigma; ++j) {
+        const int lj = slen[j];
+        rank += (lj > len) || (lj == len && j < (int)threadIdx.x);
+    }
+    slot_row[(int64_t)blockIdx.x * sigma + rank] = (row < D) ? (int)row : -1;
+}
+
+__global__ void k_sell_sizes(int64_t nslices, const int* __restrict__ rowptr, const int* __restrict__ slot_row,
+                             int* __restrict__ sizes)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslices) return;
     int w = 0;
-    for (int64_t r = s << 5; r < min((s << 5) + 32, D); ++r) w = max(w, rowptr[r + 1] - rowptr[r]);
+    for (int q = 0; q < 32; ++q) {
+        const int r = slot_row[(s << 5) + q];
+        if (r >= 0) w = max(w, rowptr[r + 1] - rowptr[r]);
+    }
     sizes[s] = w << 5;
 }
 
 __global__ void k_sell_fill(int64_t D, int64_t nslices, const int* __restrict__ rowptr, const int* __restrict__ col,
-                            const double* __restrict__ valJ, const int* __restrict__ sptr, int* __restrict__ scol,
-                            double* __restrict__ sval, int* __restrict__ sdiag)
+                            const double* __restrict__ valJ, const int* __restrict__ slot_row, const int* __restrict__ sptr,
+                            int* __restrict__ scol, double* __restrict__ sval, int* __restrict__ sdiag)
 {
     const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (s >= nslices) return;
     const int lane = threadIdx.x & 31;
-    const int64_t r = (s << 5) + lane;
+    const int r = slot_row[(s << 5) + lane];
     const int base = sptr[s], w = (sptr[s + 1] - base) >> 5;
     int a = 0, len = 0;
-    if (r < D) {
+    if (r >= 0) {
         a = rowptr[r];
         len = rowptr[r + 1] - a;
     }
-    const int self = (int)min(r, D - 1);
+    const int self = (r >= 0) ? r : (int)min((s << 5) + lane, D - 1);
     for (int j = 0; j < w; ++j) {
         int c = self;
         double v = 0.0;
         if (j < len) {
             c = col[a + j];
             v = valJ[a + j];
-            if (c == (int)r) sdiag[r] = base + (j << 5) + lane;
+            if (c == r) sdiag[r] = base + (j << 5) + lane;
         }
         scol[base + (j << 5) + lane] = c;
         sval[base + (j << 5) + lane] = v;
@@ -321,12 +343,16 @@ __global__ void k_sell_diag(int64_t D, int n, const int* __restrict__ sdiag, con
 static int build_sell(bh_ctx* ctx)
 {
     const int64_t D = ctx->D;
-    const int64_t ns = (D + 31) / 32;
+    const int sigma = ctx->sell_sigma;  // 32 = no sorting beyond the slice itself
+    const int64_t nwin = (D + sigma - 1) / sigma;
+    const int64_t ns = nwin * (sigma / 32);
     int* d_sizes = nullptr;
     BH_CUDA(ctx, cudaMalloc(&d_sizes, sizeof(int) * ns));
     BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_ptr, sizeof(int) * (ns + 1)));
-    k_sell_sizes<<<nblocks(ns, 256), 256, 0, ctx->stream>>>(D, ns, ctx->d_rowptr, d_sizes);
-    BH_LAUNCHED(ctx);
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_row, sizeof(int) * ns * 32));
+    k_sell_perm<<<(int)nwin, sigma, sizeof(int) * sigma, ctx->stream>>>(D, sigma, ctx->d_rowptr, ctx->d_sell_row);
+    k_sell_sizes<<<nblocks(ns, 256), 256, 0, ctx->stream>>>(ns, ctx->d_rowptr, ctx->d_sell_row, d_sizes);
+    ctx->launches += 2;
     int64_t total = 0;
     BH_TRY(exclusive_scan(ctx, ns, d_sizes, ctx->d_sell_ptr, &total));
     cudaFree(d_sizes);
@@ -338,8 +364,8 @@ static int build_sell(bh_ctx* ctx)
     BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_valH, sizeof(double) * std::max<int64_t>(total, 1)));
     BH_CUDA(ctx, cudaMalloc(&ctx->d_sell_diag, sizeof(int) * D));
     BH_CUDA(ctx, cudaMemsetAsync(ctx->d_sell_diag, 0, sizeof(int) * D, ctx->stream));
-    k_sell_fill<<<nblocks(ns, 8), 256, 0, ctx->stream>>>(D, ns, ctx->d_rowptr, ctx->d_col, ctx->d_valJ, ctx->d_sell_ptr,
-                                                         ctx->d_sell_col, ctx->d_sell_valJ, ctx->d_sell_diag);
+    k_sell_fill<<<nblocks(ns, 8), 256, 0, ctx->stream>>>(D, ns, ctx->d_rowptr, ctx->d_col, ctx->d_valJ, ctx->d_sell_row,
+                                                         ctx->d_sell_ptr, ctx->d_sell_col, ctx->d_sell_valJ, ctx->d_sell_diag);
     BH_LAUNCHED(ctx);
     BH_CUDA(ctx, cudaGetLastError());
     ctx->sell_valid = false;

@@ -60,6 +60,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     ctx->own_stream = true;
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
     if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
+    if (const char* v = getenv("BH_SELL_SIGMA")) ctx->sell_sigma = std::min(1024, std::max(32, atoi(v) / 32 * 32));
     if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
     if (const char* v = getenv("BH_COMPRESS_TILED")) ctx->compress_tiled = atoi(v);
     if (const char* v = getenv("BH_CHEB_DEGREE")) ctx->cheb_degree = std::max(1, atoi(v));
@@ -89,6 +90,7 @@ int bh_release_system(bh_ctx* ctx)
     free_dev(ctx->d_valJ); ctx->d_valJ = nullptr;
     free_dev(ctx->d_diagpos); ctx->d_diagpos = nullptr;
     free_dev(ctx->d_valH); ctx->d_valH = nullptr;
+    free_dev(ctx->d_sell_row); ctx->d_sell_row = nullptr;
     free_dev(ctx->d_sell_ptr); ctx->d_sell_ptr = nullptr;
     free_dev(ctx->d_sell_col); ctx->d_sell_col = nullptr;
     free_dev(ctx->d_sell_valJ); ctx->d_sell_valJ = nullptr;

@@ -202,10 +202,16 @@ __global__ void k_tile_cap(int64_t D, const int* __restrict__ rowptr, int* __res
 // Index / value loads are perfectly coalesced streaming loads (evict-first), no shared memory, full
 // occupancy; each lane accumulates its row in column order with FMAs.
 // ---------------------------------------------------------------------------------------------
-#define SELL_BATCH 8
-__global__ void __launch_bounds__(256)
-k_hv_sell(int64_t D, int64_t nslices, const int* __restrict__ sptr, const int* __restrict__ scol,
-          const double* __restrict__ sval, const double* __restrict__ x, double* __restrict__ y, BhEpilogue ep)
+#ifndef SELL_BATCH
+#define SELL_BATCH 12
+#endif
+#ifndef SELL_MINB
+#define SELL_MINB 4
+#endif
+__global__ void __launch_bounds__(256, SELL_MINB)
+k_hv_sell(int64_t D, int64_t nslices, const int* __restrict__ sptr, const int* __restrict__ srow,
+          const int* __restrict__ scol, const double* __restrict__ sval, const double* __restrict__ x,
+          double* __restrict__ y, BhEpilogue ep)
 {
     const int lane = threadIdx.x & 31;
     const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -226,8 +232,8 @@ k_hv_sell(int64_t D, int64_t nslices, const int* __restrict__ sptr, const int* _
 #pragma unroll
             for (int u = 0; u < SELL_BATCH; ++u) acc = fma(v[u], xv[u], acc);
         }
-        const int64_t r = (s << 5) + lane;
-        if (r < D) {
+        const int r = __ldg(srow + (s << 5) + lane);  // sigma-sorted slot -> row
+        if (r >= 0) {
             double out = ep.s1 * acc;
             if (ep.s2 != 0.0) out = fma(ep.s2, x[r], out);
             if (ep.z) out = fma(ep.s3, ep.z[r], out);
@@ -512,7 +518,7 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, cons
         if (kernel == BH_HV_STORED) BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu));
         const int64_t ns = ctx->sell_nslices;
         const int grid = (int)std::min<int64_t>((ns + 7) / 8, (int64_t)ctx->sm_count * 8);
-        k_hv_sell<<<grid, 256, 0, ctx->stream>>>(D, ns, ctx->d_sell_ptr, ctx->d_sell_col, ctx->d_sell_valH, x, y, ep);
+        k_hv_sell<<<grid, 256, 0, ctx->stream>>>(D, ns, ctx->d_sell_ptr, ctx->d_sell_row, ctx->d_sell_col, ctx->d_sell_valH, x, y, ep);
         fused = true;
         BH_LAUNCHED(ctx);
     } else if (kernel == BH_HV_STORED) {
