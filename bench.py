@@ -6,8 +6,9 @@
 Workload (config 3 of BASELINE.json, SURVEY.md section 8d "C3"): closed chain m = 12 sites, n = 12 bosons
 (D = 1 352 078, nnz(H) = 18 282 446), the 32 x 32 grid of `-J 1 -U 0 -u 0 -r 31 -s 1 -f J`
 (J-coefficient 1, U-coefficient 1..32, mu 0..31).  A step = one batch of P grid points per GPU (eigensolve for
-the 20 lowest levels + gap ratio + SPDM + condensate fraction + coherence), points drawn from a fixed
-permutation of the 1024 grid indices; per-GPU work is fixed as N grows (weak scaling, no data-path collective).
+the 20 lowest levels + gap ratio + SPDM + condensate fraction + coherence); every rank gets the same U values (a fixed
+pseudo-random order over the grid's 32) at different mu; per-GPU work is fixed as N grows (weak scaling, no data-path
+collective).
 
   value     points/s, whole job, basis + stored H resident in HBM, timed with CUDA events on the launching stream
   e2e       points/s through the C ABI from a cold context: bh_setup + bh_points with host buffers, wall clock,
@@ -162,6 +163,7 @@ def main():
     ap.add_argument("--full-matvecs", type=int, default=REF_MEAN_MATVECS,
                     help="H.v count of a converged C3 solve used to scale the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the m=n=14 matrix-free H.v timing")
     ap.add_argument("--m", type=int, default=12)
     ap.add_argument("--n", type=int, default=12)
     args = ap.parse_args()
@@ -189,10 +191,17 @@ def main():
     kernel = capi.HV_STORED if args.kernel == "stored" else capi.HV_MATRIX_FREE
 
     cJ, cU, cmu = grid_points()
-    perm = np.random.default_rng(0).permutation(GRID * GRID)
+    uperm = np.random.default_rng(0).permutation(GRID)
 
     def step_points(s):
-        idx = [perm[((s * N + rank) * P + q) % (GRID * GRID)] for q in range(P)]
+        """Grid points of step s on this rank: every rank gets the same U values (fixed pseudo-random order over the 32
+        of the grid) at different mu values, so the per-rank work is equal by construction -- on the real grid every U
+        occurs with all 32 mu, and the cost of a point does not depend on mu (a pure shift of the spectrum)."""
+        idx = []
+        for q in range(P):
+            iu = int(uperm[(s * P + q) % GRID])
+            imu = (rank + s * P + q) % GRID
+            idx.append(iu * GRID + imu)
         return cJ[idx], cU[idx], cmu[idx]
 
     # a dedicated (non-null) stream: the library launches on it and the CUDA events are recorded on it
@@ -283,7 +292,38 @@ def main():
         ctx.hv(1.0, 4.0, 1.0, xh, kernel=capi.HV_STORED, order=capi.LEX)
     hv_host_ms = (time.perf_counter() - t0) / 5 * 1e3
 
+    # config 5 shape for the record (N = 1 only): matrix-free H.v at m = n = 14, algorithmic bytes 16 D
+    c5 = None
+    if world == 1 and not args.no_c5:
+        try:
+            c14 = pkg.Context(local)
+            c14.set_stream(stream.cuda_stream)
+            c14.setup(14, 14)
+            D14 = c14.D
+            x14 = torch.empty(D14, dtype=torch.float64, device="cuda")
+            y14 = torch.empty(D14, dtype=torch.float64, device="cuda")
+            c14.lcg_fill_dev(x14.data_ptr(), D14)
+            for _ in range(3):
+                c14.hv_dev(1.0, 4.0, 1.0, x14.data_ptr(), y14.data_ptr(), capi.HV_MATRIX_FREE)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(10):
+                c14.hv_dev(1.0, 4.0, 1.0, x14.data_ptr(), y14.data_ptr(), capi.HV_MATRIX_FREE)
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms14 = a.elapsed_time(b) / 10
+            ab14 = c14.hv_algorithmic_bytes(capi.HV_MATRIX_FREE)
+            c5 = {"workload": "C5 shape: closed chain m=14 n=14 (D=20058300), matrix-free H.v", "ms": ms14,
+                  "algorithmic_bytes": ab14, "gbs": ab14 / (ms14 * 1e-3) / 1e9}
+            c14.close()
+            del x14, y14
+        except Exception as ex:
+            c5 = {"error": str(ex)}
+
     peak, peak_src = peaks()
+    if c5 and "gbs" in c5:
+        c5["frac_of_hbm_peak"] = c5["gbs"] / peak
     traffic = None
     tf = os.path.join(ROOT, "profiles", "hv_traffic.json")
     if os.path.exists(tf):
@@ -321,7 +361,10 @@ def main():
                    "l2": "inputs larger than L2 (Krylov basis 454 MB per point; stored H 433 MB for the roofline kernel)",
                    "mean_matvecs_per_point": int(np.mean(matvecs)) if matvecs else None, "setup_seconds": setup_s},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "hv": {"stored": hv["stored"], "matrix_free": hv["matrix_free"], "host_vectors_ms": hv_host_ms},
+        "hv": {"stored": hv["stored"], "matrix_free": hv["matrix_free"], "host_vectors_ms": hv_host_ms,
+               "note": "roofline = the stored H.v the metric names (C3); the sweep itself runs the matrix-free chain kernel "
+                       "(instruction-bound, 8x less HBM traffic), whose 16*D figure is listed here and for C5 below"},
+        "c5_matrix_free_hv": c5,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
