@@ -82,6 +82,10 @@ runs = {
     "phase_m5_fu.txt": ["-m", 5, "-n", 5, "-J", 0.5, "-U", 2, "-u", 1, "-r", 1, "-s", 0.5, "-f", "u", "-t", "exact"],
     "phase_m6_fJ.txt": ["-m", 6, "-n", 6, "-J", 1, "-U", 0, "-u", 0, "-r", 3, "-s", 1, "-f", "J", "-t", "exact"],
     "phase_m8_fJ.txt": ["-m", 8, "-n", 8, "-J", 1, "-U", 0, "-u", 0, "-r", 2, "-s", 1, "-f", "J", "-t", "exact"],
+    # config 1 of BASELINE.json in full (121 points) and a 3 x 3 corner of config 2 (85 s: the reference's thread
+    # heuristic leaves it single-threaded at m = n = 10)
+    "phase_m8_C1.txt": ["-m", 8, "-n", 8, "-J", 1, "-U", 0, "-u", 0, "-r", 10, "-s", 1, "-f", "J", "-t", "exact"],
+    "phase_m10_fJ.txt": ["-m", 10, "-n", 10, "-J", 1, "-U", 0, "-u", 0, "-r", 2, "-s", 1, "-f", "J", "-t", "exact"],
 }
 for name, args in runs.items():
     open(os.path.join(HERE, name), "w").write(R.cli_phase(args, threads=8))

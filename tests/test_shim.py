@@ -95,6 +95,8 @@ CLI_RUNS = {
     "phase_m5_fu.txt": ["-m", 5, "-n", 5, "-J", 0.5, "-U", 2, "-u", 1, "-r", 1, "-s", 0.5, "-f", "u", "-t", "exact"],
     "phase_m6_fJ.txt": ["-m", 6, "-n", 6, "-J", 1, "-U", 0, "-u", 0, "-r", 3, "-s", 1, "-f", "J", "-t", "exact"],
     "phase_m8_fJ.txt": ["-m", 8, "-n", 8, "-J", 1, "-U", 0, "-u", 0, "-r", 2, "-s", 1, "-f", "J", "-t", "exact"],
+    "phase_m8_C1.txt": ["-m", 8, "-n", 8, "-J", 1, "-U", 0, "-u", 0, "-r", 10, "-s", 1, "-f", "J", "-t", "exact"],   # BASELINE config 1
+    "phase_m10_fJ.txt": ["-m", 10, "-n", 10, "-J", 1, "-U", 0, "-u", 0, "-r", 2, "-s", 1, "-f", "J", "-t", "exact"],
 }
 
 
@@ -112,7 +114,8 @@ def test_cli_phase_txt(name):
     assert np.array_equal(g[:, :2], w[:, :2])
     assert np.allclose(g[:, 2:], w[:, 2:], rtol=2e-6, atol=1e-9)   # 6 significant digits in the file
     same_text = sum(a == b for a, b in zip(got.split("\n"), want.split("\n")))
-    assert same_text >= len(want.split("\n")) - 1                  # text identical up to one last-digit rounding
+    # text identical up to a last-digit rounding in at most 1 % of the rows
+    assert same_text >= len(want.split("\n")) - 1 - len(want.split("\n")) // 100
 
 
 def test_cli_validation_messages():
