@@ -88,14 +88,19 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
     std::exception_ptr failure;
     std::mutex mtx;
 
+    // In the -f J and -f U modes the second swept parameter multiplies uH = -N*I (src/analysis.cpp:245-251): it only
+    // shifts the spectrum, eigenvectors and all three output columns are unchanged.  With
+    // opt.reuse_shift the row j = 0 is solved and copied to the other j (exact identity, opt-in, off by default).
+    const bool shift_rows = opt.reuse_shift && g.fixed != "u";
+    const int ntasks = shift_rows ? g.num1 : total;
     while (true) {
         std::atomic<int> next(0), done(0);
         auto worker = [&](int d) {
             try {
                 for (;;) {
                     const int t = next.fetch_add(1);
-                    if (t >= total) break;
-                    const int i = t / g.num2, j = t % g.num2;
+                    if (t >= ntasks) break;
+                    const int i = shift_rows ? t : t / g.num2, j = shift_rows ? 0 : t % g.num2;
                     const double p1 = g.p1_min + i * g.step1;
                     const double p2 = g.p2_min + j * g.step2;
                     double cJ, cU, cmu, out3[3];
@@ -103,10 +108,14 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
                     const int rc = bh_point(ctxs[d], cJ, cU, cmu, nb_eigen, opt.kernel, out3, nullptr, nullptr, nullptr);
                     if (rc == BH_ERR_ARG) throw std::invalid_argument(bh_last_error(ctxs[d]));
                     if (rc != BH_OK) throw std::runtime_error(bh_last_error(ctxs[d]));
-                    const int index = i * g.num1 + j;  // src/analysis.cpp:341 (sic)
                     std::lock_guard<std::mutex> lk(mtx);
-                    if (index >= 0 && index < total) res[index] = Analysis::SweepPoint{p1, p2, out3[0], out3[1], out3[2]};
-                    const int c = ++done;
+                    for (int jj = j; jj < (shift_rows ? g.num2 : j + 1); ++jj) {
+                        const int index = i * g.num1 + jj;  // src/analysis.cpp:341 (sic)
+                        if (index >= 0 && index < total)
+                            res[index] = Analysis::SweepPoint{p1, g.p2_min + jj * g.step2, out3[0], out3[1], out3[2]};
+                        ++done;
+                    }
+                    const int c = done.load();
                     if (opt.progress) {
                         const int progress = (c * bar_width) / total;
                         std::cout << "\rProgress: [" << std::string(progress, '#') << std::string(bar_width - progress, ' ') << "] "

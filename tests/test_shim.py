@@ -125,3 +125,13 @@ def test_cli_validation_messages():
     assert p.returncode == 1 and "s must be smaller than r" in p.stderr
     p = subprocess.run([CLI, "-t", "exact", "-m", "5", "-n", "5", "-J", "1", "-r", "2", "-s", "1", "-f", "x"], capture_output=True, text=True)
     assert p.returncode == 1 and "fixed parameter must be J, U or u" in p.stderr
+
+
+def test_cli_reuse_shift_is_exact():
+    # opt-in: the mu direction of a -f J sweep is a pure spectral shift (KA5) -> same file from num1 solves
+    with tempfile.TemporaryDirectory() as td:
+        args = [str(a) for a in CLI_RUNS["phase_m8_fJ.txt"]]
+        p = subprocess.run([CLI] + args + ["--reuse-shift", "--no-plot"], cwd=td, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0
+        got = open(os.path.join(td, "phase.txt")).read()
+    assert got == open(os.path.join(GOLD, "phase_m8_fJ.txt")).read()
