@@ -60,6 +60,17 @@ int main(int argc, char** argv)
                                                   term == "u" ? 1 : 0);
             dump_csc(argv[6], H);
             printf("{\"D\": %ld, \"nnz\": %ld}\n", (long)H.rows(), (long)H.nonZeros());
+        } else if (cmd == "maxbasis") {  // maxbasis m n out
+            auto tb = BH::max_set_basis(atoi(argv[2]), atoi(argv[3]));
+            dump(argv[4], "tags", tb.first.data(), tb.first.size());
+            dump(argv[4], "basis", tb.second.data(), tb.second.size());
+            printf("{\"D\": %ld}\n", (long)tb.first.size());
+        } else if (cmd == "maxham") {  // maxham m nmin nmax J U u lattice out
+            const int m = atoi(argv[2]);
+            auto nei = lattice(argv[8], m);
+            auto H = BH::max_bosons_hamiltonian(nei, m, atoi(argv[3]), atoi(argv[4]), atof(argv[5]), atof(argv[6]), atof(argv[7]));
+            dump_csc(argv[9], H);
+            printf("{\"D\": %ld, \"nnz\": %ld}\n", (long)H.rows(), (long)H.nonZeros());
         } else if (cmd == "eigs") {  // eigs m n cJ cU cu nev lattice out : the calls of src/analysis.cpp:231-236,311,314
             const int m = atoi(argv[2]), n = atoi(argv[3]);
             const double cJ = atof(argv[4]), cU = atof(argv[5]), cu = atof(argv[6]);

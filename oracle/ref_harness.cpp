@@ -234,6 +234,27 @@ int main(int argc, char** argv)
                (t1 - t0) / (reps > 0 ? reps : 1), reps);
         return 0;
     }
+    if (cmd == "maxbasis") {
+        // maxbasis m n out : BH::max_set_basis (src/hamiltonian.cpp:152-166), all boson numbers 1..n, tag-sorted
+        int m = atoi(argv[2]), n = atoi(argv[3]);
+        std::string out = argv[4];
+        auto tb = BH::max_set_basis(m, n);
+        dump(out, "tags", tb.first.data(), tb.first.size());
+        dump(out, "basis", tb.second.data(), tb.second.size());
+        printf("{\"D\": %ld}\n", (long)tb.first.size());
+        return 0;
+    }
+    if (cmd == "maxham") {
+        // maxham m nmin nmax J U u lattice out : BH::max_bosons_hamiltonian (src/hamiltonian.cpp:260-288)
+        int m = atoi(argv[2]), nmin = atoi(argv[3]), nmax = atoi(argv[4]);
+        double J = atof(argv[5]), U = atof(argv[6]), mu = atof(argv[7]);
+        std::string lat = argv[8], out = argv[9];
+        auto nei = lattice(lat, m);
+        Eigen::SparseMatrix<double> H = BH::max_bosons_hamiltonian(nei, m, nmin, nmax, J, U, mu);
+        dump_csc(out, H);
+        printf("{\"D\": %ld, \"nnz\": %ld}\n", (long)H.rows(), (long)H.nonZeros());
+        return 0;
+    }
     if (cmd == "partial") {
         // partial m n cJ cU cu maxit threads lattice
         // Bounded sample of one grid point for the CPU baseline at sizes where a full solve takes minutes:

@@ -46,6 +46,13 @@ for (m, n) in [(8, 8), (10, 10)]:
     (o, i, v), info = R.csc(m, n, "J")
     gold[f"cscsum_J_{m}_{n}"] = checksum_csc(o, i, v)
 
+# --- variable-N API: max_set_basis / max_bosons_hamiltonian ---
+t, b = R.max_basis(4, 3)
+gold["maxbasis_4_3_tags"], gold["maxbasis_4_3_states"] = t, b.astype(np.int8)
+for term, (J, U, mu) in {"J": (1, 0, 0), "U": (0, 1, 0), "u": (0, 0, 1)}.items():
+    o, i, v = R.max_hamiltonian(4, 1, 3, J, U, mu)
+    gold[f"maxham_{term}_4_1_3_outer"], gold[f"maxham_{term}_4_1_3_inner"], gold[f"maxham_{term}_4_1_3_val"] = o, i, v
+
 # --- H.v through Spectra's MatOp ---
 for (m, n) in [(6, 6), (8, 8)]:
     r, _ = R.hv(m, n, 1.0, 4.0, 1.0)

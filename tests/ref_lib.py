@@ -81,6 +81,17 @@ def points(m, n, fixed, cfix, p1min, p2min, step, n1, n2, threads=0, lattice="ch
     return r, info
 
 
+def max_basis(m, n):
+    info, r = _run(HARNESS, ["maxbasis", m, n, "@out"], [("tags", np.float64), ("basis", np.float64)])
+    return r["tags"], r["basis"].reshape(-1, m)
+
+
+def max_hamiltonian(m, nmin, nmax, J, U, mu, lattice="chain"):
+    info, r = _run(HARNESS, ["maxham", m, nmin, nmax, J, U, mu, lattice, "@out"],
+                   [("outer", np.int32), ("inner", np.int32), ("val", np.float64)])
+    return r["outer"], r["inner"], r["val"]
+
+
 def partial(m, n, cJ, cU, cu, maxit, threads=0, lattice="chain", timeout=7200):
     info, _ = _run(HARNESS, ["partial", m, n, cJ, cU, cu, maxit, threads, lattice], [], timeout=timeout)
     return info

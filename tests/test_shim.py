@@ -135,3 +135,16 @@ def test_cli_reuse_shift_is_exact():
         assert p.returncode == 0
         got = open(os.path.join(td, "phase.txt")).read()
     assert got == open(os.path.join(GOLD, "phase_m8_fJ.txt")).read()
+
+
+def test_variable_n_api_against_reference():
+    # BH::max_set_basis / BH::max_bosons_hamiltonian (src/hamiltonian.cpp:152-166, 260-288) vs the compiled reference
+    G = np.load(os.path.join(GOLD, "reference_golden.npz"))
+    _, r = run_shim(["maxbasis", 4, 3, "@out"], [("tags", np.float64), ("basis", np.float64)])
+    assert (bits(r["tags"]) == bits(G["maxbasis_4_3_tags"])).all()
+    assert (r["basis"].reshape(-1, 4) == G["maxbasis_4_3_states"]).all()
+    for term, (J, U, mu) in {"J": (1, 0, 0), "U": (0, 1, 0), "u": (0, 0, 1)}.items():
+        _, r = run_shim(["maxham", 4, 1, 3, J, U, mu, "chain", "@out"],
+                        [("outer", np.int32), ("inner", np.int32), ("val", np.float64)])
+        for nm in ("outer", "inner", "val"):
+            assert (r[nm] == G[f"maxham_{term}_4_1_3_{nm}"]).all(), (term, nm)
