@@ -190,6 +190,8 @@ __global__ void k_row_fill(const BhTables* __restrict__ gtab, int64_t D, const u
 
 int bh_build_hamiltonian(bh_ctx* ctx)
 {
+    if (ctx->d_rowptr) return BH_OK;  // built lazily, once (the matrix-free paths never need it)
+    if (ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "a row-partitioned context has no stored matrix");
     const int64_t D = ctx->D;
     int* d_len = nullptr;
     BH_CUDA(ctx, cudaMalloc(&d_len, sizeof(int) * D));
@@ -246,6 +248,7 @@ __global__ void k_materialise(int64_t D, int n, const int* __restrict__ rowptr, 
 
 int bh_materialise_H(bh_ctx* ctx, double cJ, double cU, double cmu)
 {
+    BH_TRY(bh_build_hamiltonian(ctx));
     if (ctx->valH_valid && ctx->cur_cJ == cJ && ctx->cur_cU == cU && ctx->cur_cmu == cmu) return BH_OK;
     const int wpb = 8;
     const int64_t nwarps = (ctx->D + 31) / 32;
@@ -342,6 +345,7 @@ __global__ void k_sell_diag(int64_t D, int n, const int* __restrict__ sdiag, con
 
 static int build_sell(bh_ctx* ctx)
 {
+    if (!ctx->user_matrix) BH_TRY(bh_build_hamiltonian(ctx));
     const int64_t D = ctx->D;
     const int sigma = ctx->sell_sigma;  // 32 = no sorting beyond the slice itself
     const int64_t nwin = (D + sigma - 1) / sigma;
@@ -471,6 +475,7 @@ static int order_maps(bh_ctx* ctx, int order, const int** perm, const int** inv)
 static int export_matrix(bh_ctx* ctx, int mode, double cJ, double cU, double cmu, int order, int32_t* outer,
                          int32_t* inner, double* val)
 {
+    BH_TRY(bh_build_hamiltonian(ctx));
     const int64_t D = ctx->D;
     const int64_t nnz = (mode == EXPORT_JTERM) ? ctx->nnzJ : ctx->nnzH;
     const int *perm, *inv;
@@ -506,6 +511,8 @@ extern "C" int bh_term_nnz(bh_ctx* ctx, int term, int64_t* nnz)
 {
     if (!ctx || !ctx->D || ctx->user_matrix || ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_term_nnz: call bh_setup first");
     if (!nnz || term < 0 || term > 2) return bh_fail(ctx, BH_ERR_ARG, "bh_term_nnz: bad argument");
+    BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    BH_TRY(bh_build_hamiltonian(ctx));
     *nnz = (term == BH_TERM_J) ? ctx->nnzJ : ctx->D;
     return BH_OK;
 }
@@ -514,6 +521,8 @@ extern "C" int bh_hamiltonian_nnz(bh_ctx* ctx, int64_t* nnz)
 {
     if (!ctx || !ctx->D || ctx->user_matrix || ctx->partitioned) return bh_fail(ctx, BH_ERR_STATE, "bh_hamiltonian_nnz: call bh_setup first");
     if (!nnz) return bh_fail(ctx, BH_ERR_ARG, "bh_hamiltonian_nnz: bad argument");
+    BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    BH_TRY(bh_build_hamiltonian(ctx));
     *nnz = ctx->nnzH;
     return BH_OK;
 }

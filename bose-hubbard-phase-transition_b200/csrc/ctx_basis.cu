@@ -437,8 +437,7 @@ static int setup_impl(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int* 
     ctx->row0 = 0;
     ctx->nloc = D;
     ctx->ld = (D + 31) / 32 * 32;
-    BH_TRY(bh_build_basis(ctx));
-    BH_TRY(bh_build_hamiltonian(ctx));
+    BH_TRY(bh_build_basis(ctx));  // the stored Hamiltonian (K2) is built on first use
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BH_OK;
 }

@@ -629,6 +629,7 @@ extern "C" int bh_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, 
 extern "C" int bh_hv_algorithmic_bytes(bh_ctx* ctx, int kernel, int64_t* bytes)
 {
     if (!ctx || !ctx->D || !bytes) return bh_fail(ctx, BH_ERR_STATE, "bh_hv_algorithmic_bytes: call bh_setup first");
+    if (kernel == BH_HV_STORED && !ctx->user_matrix) BH_TRY(bh_build_hamiltonian(ctx));
     if (kernel == BH_HV_STORED || kernel == BH_HV_USER)
         *bytes = 12 * ctx->nnzH + 4 * (ctx->D + 1) + 16 * ctx->D;
     else
