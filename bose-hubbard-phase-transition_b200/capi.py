@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("BH_B200_LIB", os.path.join(HERE, "libbh_b200.so"))  #
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOCONV, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 LEX, TAG_SORTED, REF_SCATTER = 0, 1, 2
 TERM_J, TERM_U, TERM_MU = 0, 1, 2
-HV_STORED, HV_MATRIX_FREE, HV_USER = 0, 1, 2
+HV_STORED, HV_MATRIX_FREE, HV_USER, HV_HYBRID = 0, 1, 2, 3
 
 # every symbol include/bh_b200.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [

@@ -66,6 +66,9 @@ struct bh_ctx {
     // SELL-32 copy of the stored H (variant 2): slices of 32 consecutive rows, column-major inside a slice,
     // padded to the longest row of the slice (padding = zero value pointing at the row's own column)
     int64_t sell_nslices = 0, sell_entries = 0;
+    double hybrid_frac = 0.35;      // BH_HV_HYBRID: fraction of the rows taken from the stored slices (env BH_HYBRID_FRAC)
+    int hybrid_sell_blocks = 3;     // ... and SELL-role CTAs out of every 8 (env BH_HYBRID_BLOCKS)
+    int64_t hyb_split = -1, hyb_slices = 0, hyb_entries = 0;
     int sell_sigma = 256;           // sorting window (rows), multiple of 32 (env BH_SELL_SIGMA; 32 = plain SELL-32)
     int* d_sell_row = nullptr;      // [nslices * 32] slot -> row (-1 = padding slot)
     int* d_sell_ptr = nullptr;      // [nslices + 1] entry offset of each slice
@@ -73,7 +76,7 @@ struct bh_ctx {
     double* d_sell_valJ = nullptr;
     double* d_sell_valH = nullptr;
     int* d_sell_diag = nullptr;     // [D] position of each row's diagonal entry
-    bool sell_valid = false;
+    bool sell_valid = false, sell_partial_valid = false;
     double sell_cJ = 0, sell_cU = 0, sell_cmu = 0;
 
     uint64_t* d_states = nullptr;  // packed occupations, LEX order
@@ -151,7 +154,7 @@ int bh_build_basis(bh_ctx* ctx);          // K1: states, dU
 int bh_build_hamiltonian(bh_ctx* ctx);    // K2: pattern, J values
 int bh_ensure_orderings(bh_ctx* ctx);     // tags, radix sort, permutations
 int bh_materialise_H(bh_ctx* ctx, double cJ, double cU, double cmu);
-int bh_materialise_sell(bh_ctx* ctx, double cJ, double cU, double cmu);  // builds the SELL copy on first use
+int bh_materialise_sell(bh_ctx* ctx, double cJ, double cU, double cmu, int64_t max_entries = -1, int64_t max_rows = -1);  // builds the SELL copy on first use
 // y = s1 * (H x) + s2 * x + s3 * z   (the epilogue is fused into the H.v kernels; plain H.v = {1, 0, 0, NULL})
 struct BhEpilogue {
     double s1 = 1.0, s2 = 0.0, s3 = 0.0;

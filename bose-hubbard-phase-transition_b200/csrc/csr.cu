@@ -376,20 +376,24 @@ static int build_sell(bh_ctx* ctx)
     return BH_OK;
 }
 
-int bh_materialise_sell(bh_ctx* ctx, double cJ, double cU, double cmu)
+int bh_materialise_sell(bh_ctx* ctx, double cJ, double cU, double cmu, int64_t max_entries, int64_t max_rows)
 {
     const int64_t D = ctx->D;
     if (!ctx->d_sell_ptr) BH_TRY(build_sell(ctx));
-    if (ctx->sell_valid && ctx->sell_cJ == cJ && ctx->sell_cU == cU && ctx->sell_cmu == cmu) return BH_OK;
-    k_sell_scale<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->sell_entries, ctx->d_sell_valJ, cJ, ctx->d_sell_valH);
-    k_sell_diag<<<nblocks(D, 256), 256, 0, ctx->stream>>>(D, ctx->n, ctx->d_sell_diag, ctx->d_sell_valJ, ctx->d_dU, cJ, cU,
+    if ((ctx->sell_valid || (max_entries >= 0 && ctx->sell_partial_valid)) && ctx->sell_cJ == cJ && ctx->sell_cU == cU && ctx->sell_cmu == cmu) return BH_OK;
+    // (the hybrid H.v only reads the slices of its stored rows: materialise just those)
+    const int64_t ne = (max_entries >= 0) ? max_entries : ctx->sell_entries;
+    const int64_t nr = (max_rows >= 0) ? max_rows : D;
+    k_sell_scale<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ne, ctx->d_sell_valJ, cJ, ctx->d_sell_valH);
+    k_sell_diag<<<nblocks(nr, 256), 256, 0, ctx->stream>>>(nr, ctx->n, ctx->d_sell_diag, ctx->d_sell_valJ, ctx->d_dU, cJ, cU,
                                                           cmu, ctx->d_sell_valH);
     ctx->launches += 2;
     BH_CUDA(ctx, cudaGetLastError());
     ctx->sell_cJ = cJ;
     ctx->sell_cU = cU;
     ctx->sell_cmu = cmu;
-    ctx->sell_valid = true;
+    ctx->sell_valid = (max_entries < 0);  // a partial materialisation does not serve the full stored kernel
+    ctx->sell_partial_valid = true;
     return BH_OK;
 }
 

@@ -60,6 +60,8 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     ctx->own_stream = true;
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
     if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
+    if (const char* v = getenv("BH_HYBRID_FRAC")) ctx->hybrid_frac = std::min(1.0, std::max(0.0, atof(v)));
+    if (const char* v = getenv("BH_HYBRID_BLOCKS")) ctx->hybrid_sell_blocks = std::min(7, std::max(1, atoi(v)));
     if (const char* v = getenv("BH_SELL_SIGMA")) ctx->sell_sigma = std::min(1024, std::max(32, atoi(v) / 32 * 32));
     if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
     if (const char* v = getenv("BH_COMPRESS_TILED")) ctx->compress_tiled = atoi(v);
@@ -98,6 +100,7 @@ int bh_release_system(bh_ctx* ctx)
     free_dev(ctx->d_sell_diag); ctx->d_sell_diag = nullptr;
     ctx->sell_valid = false;
     ctx->sell_nslices = ctx->sell_entries = 0;
+    ctx->hyb_split = -1;
     free_dev(ctx->d_tags); ctx->d_tags = nullptr;
     free_dev(ctx->d_perm_tag); ctx->d_perm_tag = nullptr;
     free_dev(ctx->d_inv_tag); ctx->d_inv_tag = nullptr;

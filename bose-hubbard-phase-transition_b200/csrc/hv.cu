@@ -404,6 +404,115 @@ static hv_free_fn_t hv_chain_kernel(int m)
     return nullptr;
 }
 
+
+// K3 + K4 hybrid for chains: rows [0, split) are taken from the stored SELL slices (HBM-bound: ~29 % of the issue slots at
+// full bandwidth), rows [split, D) are re-derived matrix-free (issue-bound, almost no HBM traffic), by different CTAs
+// of ONE launch, interleaved so that every SM runs both roles: the memory system and the issue slots are busy together.
+template <int M, bool CLOSED>
+__global__ void __launch_bounds__(256, 4)
+k_hv_hybrid(const BhTables* __restrict__ gtab, int64_t D, int64_t split, int64_t nsl, int ks, const int* __restrict__ sptr,
+            const int* __restrict__ srow, const int* __restrict__ scol, const double* __restrict__ sval,
+            const uint64_t* __restrict__ states, const double* __restrict__ dU, double cJ, double cU, double cmu,
+            const double* __restrict__ x, double* __restrict__ y, BhEpilogue ep)
+{
+    const int period = 8;
+    const int grp = blockIdx.x / period, pos = blockIdx.x % period, ngrp = gridDim.x / period;
+    if (pos < ks) {
+        // ---- stored role ----
+        const int lane = threadIdx.x & 31;
+        const int64_t nw = (int64_t)ngrp * ks * (blockDim.x >> 5);
+        for (int64_t s = ((int64_t)grp * ks + pos) * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nsl; s += nw) {
+            const int base = __ldg(sptr + s), end = __ldg(sptr + s + 1);
+            double acc = 0.0;
+            for (int p = base + lane; p < end; p += 32 * SELL_BATCH) {
+                int c[SELL_BATCH];
+                double v[SELL_BATCH], xv[SELL_BATCH];
+#pragma unroll
+                for (int u = 0; u < SELL_BATCH; ++u) {
+                    const bool ok = p + 32 * u < end;
+                    c[u] = ok ? __ldcs(scol + p + 32 * u) : -1;
+                    v[u] = ok ? __ldcs(sval + p + 32 * u) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < SELL_BATCH; ++u) xv[u] = (c[u] >= 0) ? __ldg(x + c[u]) : 0.0;
+#pragma unroll
+                for (int u = 0; u < SELL_BATCH; ++u) acc = fma(v[u], xv[u], acc);
+            }
+            const int r = __ldg(srow + (s << 5) + lane);
+            if (r >= 0) {
+                double out = ep.s1 * acc;
+                if (ep.s2 != 0.0) out = fma(ep.s2, x[r], out);
+                if (ep.z) out = fma(ep.s3, ep.z[r], out);
+                y[r] = out;
+            }
+        }
+        return;
+    }
+    // ---- matrix-free role ----
+    __shared__ BhTables t;
+    bh_stage_tables(&t, gtab);
+    const double shift = __dmul_rn(-(double)t.n, cmu);
+    const int kc = period - ks;
+    const int64_t nthreads = (int64_t)ngrp * kc * blockDim.x;
+    for (int64_t k = split + ((int64_t)grp * kc + (pos - ks)) * blockDim.x + threadIdx.x; k < D; k += nthreads) {
+        const uint64_t s = states[k];
+        const int kk = (int)k;
+        const int n0 = bh_occ(s, 0);
+        int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < M - 1; ++q) {
+            const int nnext = bh_occ(s, q + 1);
+            const int2 gh = t.gh[q][R];
+            const double xa = nnext ? __ldg(x + (kk + gh.x)) : 0.0;
+            const double xb = nprev ? __ldg(x + (kk + gh.y)) : 0.0;
+            acc = fma(t.sq[(nprev + 1) * nnext], xa, acc);
+            acc = fma(t.sq[(nnext + 1) * nprev], xb, acc);
+            tdn += gh.x;
+            tup += gh.y;
+            R -= nnext;
+            nprev = nnext;
+        }
+        if (CLOSED) {
+            const int nl = nprev;
+            const double xa = nl ? __ldg(x + (kk + tdn)) : 0.0;
+            const double xb = n0 ? __ldg(x + (kk + tup)) : 0.0;
+            acc = fma(t.sq[(n0 + 1) * nl], xa, acc);
+            acc = fma(t.sq[(nl + 1) * n0], xb, acc);
+        }
+        const double diag = __dadd_rn(__dmul_rn(dU[k], cU), shift);
+        const double xv = x[k];
+        double out = ep.s1 * (diag * xv - (2.0 * cJ) * acc);
+        if (ep.s2 != 0.0) out = fma(ep.s2, xv, out);
+        if (ep.z) out = fma(ep.s3, ep.z[k], out);
+        y[k] = out;
+    }
+}
+
+typedef void (*hv_hybrid_fn_t)(const BhTables*, int64_t, int64_t, int64_t, int, const int*, const int*, const int*, const double*,
+                               const uint64_t*, const double*, double, double, double, const double*, double*, BhEpilogue);
+template <bool CLOSED>
+static hv_hybrid_fn_t hv_hybrid_kernel(int m)
+{
+    switch (m) {
+        case 3: return k_hv_hybrid<3, CLOSED>;
+        case 4: return k_hv_hybrid<4, CLOSED>;
+        case 5: return k_hv_hybrid<5, CLOSED>;
+        case 6: return k_hv_hybrid<6, CLOSED>;
+        case 7: return k_hv_hybrid<7, CLOSED>;
+        case 8: return k_hv_hybrid<8, CLOSED>;
+        case 9: return k_hv_hybrid<9, CLOSED>;
+        case 10: return k_hv_hybrid<10, CLOSED>;
+        case 11: return k_hv_hybrid<11, CLOSED>;
+        case 12: return k_hv_hybrid<12, CLOSED>;
+        case 13: return k_hv_hybrid<13, CLOSED>;
+        case 14: return k_hv_hybrid<14, CLOSED>;
+        case 15: return k_hv_hybrid<15, CLOSED>;
+        case 16: return k_hv_hybrid<16, CLOSED>;
+    }
+    return nullptr;
+}
+
 typedef void (*hv_free_fn)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double, double, double,
                            const double*, double*);
 
@@ -505,11 +614,41 @@ __global__ void k_epilogue(int64_t n, double* __restrict__ y, const double* __re
     }
 }
 
-int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x, double* y, const BhEpilogue& ep)
+int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, const double* x, double* y, const BhEpilogue& ep)
 {
+    int kernel = kernel_in;
     bool fused = false;
     const bool plain = (ep.s1 == 1.0 && ep.s2 == 0.0 && ep.z == nullptr);
     const int64_t D = ctx->D;
+    if (kernel == BH_HV_HYBRID) {
+        // only for chains on a single GPU; everything else runs the matrix-free kernel
+        if (ctx->partitioned || ctx->user_matrix || !ctx->h_tab.chain || ctx->hybrid_frac <= 0.0) {
+            kernel = BH_HV_MATRIX_FREE;
+        } else {
+            const int64_t Dh = ctx->D;
+            if (ctx->hyb_split < 0) {
+                BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu));  // builds the SELL copy
+                const int64_t win = ctx->sell_sigma;
+                int64_t split = (int64_t)(ctx->hybrid_frac * (double)Dh) / win * win;
+                split = std::min(split, Dh / win * win);
+                ctx->hyb_split = split;
+                ctx->hyb_slices = split / 32;
+                int ent = 0;
+                BH_D2H(ctx, &ent, ctx->d_sell_ptr + ctx->hyb_slices, sizeof(int));
+                BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                ctx->hyb_entries = ent;
+            }
+            BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu, ctx->hyb_entries, ctx->hyb_split));
+            hv_hybrid_fn_t fn = (ctx->h_tab.chain == 2) ? hv_hybrid_kernel<true>(ctx->m) : hv_hybrid_kernel<false>(ctx->m);
+            const int grid = ctx->sm_count * 8;  // a multiple of the role period (8)
+            fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, Dh, ctx->hyb_split, ctx->hyb_slices, ctx->hybrid_sell_blocks, ctx->d_sell_ptr,
+                                              ctx->d_sell_row, ctx->d_sell_col, ctx->d_sell_valH, ctx->d_states, ctx->d_dU, cJ, cU, cmu,
+                                              x, y, ep);
+            BH_LAUNCHED(ctx);
+            BH_CUDA(ctx, cudaGetLastError());
+            return BH_OK;
+        }
+    }
     if (ctx->partitioned && kernel != BH_HV_MATRIX_FREE)
         return bh_fail(ctx, BH_ERR_STATE, "a row-partitioned context has no stored matrix: use BH_HV_MATRIX_FREE");
     if (ctx->user_matrix != (kernel == BH_HV_USER))

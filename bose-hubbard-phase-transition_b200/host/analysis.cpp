@@ -17,6 +17,7 @@
 #include <limits>
 #include <mutex>
 #include <numeric>
+#include <sstream>
 #include <stdexcept>
 #include <thread>
 
@@ -91,6 +92,33 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
     // In the -f J and -f U modes the second swept parameter multiplies uH = -N*I (src/analysis.cpp:245-251): it only
     // shifts the spectrum, eigenvectors and all three output columns are unchanged.  With
     // opt.reuse_shift the row j = 0 is solved and copied to the other j (exact identity, opt-in, off by default).
+    // Checkpoint / resume (the reference writes phase.txt only after the whole grid, src/analysis.cpp:384-387): with
+    // opt.resume every finished point is appended to "<output>.partial" (index + the five columns, 17 significant
+    // digits) and points found there are not recomputed.  The file is tied to the sweep by a header line.
+    const std::string partial_path = opt.output + ".partial";
+    std::vector<char> have(total, 0);
+    std::ofstream partial;
+    if (opt.resume) {
+        std::ostringstream hdr;
+        hdr << "# m " << m << " n " << n << " fixed " << g.fixed << " " << std::setprecision(17) << g.fixed_value << " grid " << g.p1_min << " "
+            << g.p2_min << " " << g.step1 << " " << g.num1 << " " << g.num2 << " nb_eigen " << nb_eigen;
+        std::ifstream in(partial_path);
+        std::string line;
+        bool ok = static_cast<bool>(std::getline(in, line)) && line == hdr.str();
+        while (ok && std::getline(in, line)) {
+            std::istringstream ls(line);
+            int index;
+            Analysis::SweepPoint p;
+            if (ls >> index >> p.param1 >> p.param2 >> p.gap_ratio >> p.condensate_fraction >> p.coherence && index >= 0 && index < total) {
+                res[index] = p;
+                have[index] = 1;
+            }
+        }
+        in.close();
+        partial.open(partial_path, ok ? std::ios::app : std::ios::trunc);
+        if (!ok) partial << hdr.str() << std::endl;
+        partial << std::setprecision(17);
+    }
     const bool shift_rows = opt.reuse_shift && g.fixed != "u";
     const int ntasks = shift_rows ? g.num1 : total;
     while (true) {
@@ -105,14 +133,31 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
                     const double p2 = g.p2_min + j * g.step2;
                     double cJ, cU, cmu, out3[3];
                     coefficients(g, p1, p2, cJ, cU, cmu);
+                    {
+                        // resume: every output row this task would produce is already there
+                        bool all = opt.resume;
+                        for (int jj = j; all && jj < (shift_rows ? g.num2 : j + 1); ++jj) {
+                            const int index = i * g.num1 + jj;
+                            all = index >= 0 && index < total && have[index];
+                        }
+                        if (all) {
+                            std::lock_guard<std::mutex> lk(mtx);
+                            done += shift_rows ? g.num2 : 1;
+                            continue;
+                        }
+                    }
                     const int rc = bh_point(ctxs[d], cJ, cU, cmu, nb_eigen, opt.kernel, out3, nullptr, nullptr, nullptr);
                     if (rc == BH_ERR_ARG) throw std::invalid_argument(bh_last_error(ctxs[d]));
                     if (rc != BH_OK) throw std::runtime_error(bh_last_error(ctxs[d]));
                     std::lock_guard<std::mutex> lk(mtx);
                     for (int jj = j; jj < (shift_rows ? g.num2 : j + 1); ++jj) {
                         const int index = i * g.num1 + jj;  // src/analysis.cpp:341 (sic)
-                        if (index >= 0 && index < total)
+                        if (index >= 0 && index < total) {
                             res[index] = Analysis::SweepPoint{p1, g.p2_min + jj * g.step2, out3[0], out3[1], out3[2]};
+                            if (opt.resume)
+                                partial << index << " " << res[index].param1 << " " << res[index].param2 << " " << out3[0] << " " << out3[1]
+                                        << " " << out3[2] << std::endl;
+                        }
                         ++done;
                     }
                     const int c = done.load();
@@ -142,6 +187,7 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
         variance /= res.size();
         if (variance > variance_threshold_percent * mean) break;
         nb_eigen += 5;
+        std::fill(have.begin(), have.end(), 0);  // the whole grid is repeated with more eigenvalues
     }
     for (bh_ctx* c : ctxs) bh_ctx_destroy(c);
     if (failure) std::rethrow_exception(failure);

@@ -10,6 +10,7 @@ namespace Analysis {
 // Options the reference hard-codes (src/analysis.cpp:219-220, :269, :277).  The defaults reproduce it.
 struct ExactOptions {
     int gpus = 0;                  // GPUs to shard the grid over (0 = every visible device)
+    bool resume = false;           // append finished points to <output>.partial and skip them when restarted
     bool reuse_shift = false;      // -f J / -f U: the second parameter only shifts the spectrum; solve each row once
     int contexts_per_gpu = 1;      // concurrent grid points per GPU (each on its own context)
     int kernel = 0;                // BH_HV_STORED (0) or BH_HV_MATRIX_FREE (1)

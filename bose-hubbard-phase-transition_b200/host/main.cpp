@@ -35,6 +35,7 @@ static void print_usage()
               << "  -o, --output    Output file (default phase.txt)\n"
               << "  -c, --concurrent Grid points solved concurrently per GPU (default 1)\n"
               << "      --no-plot   Do not run plot.py afterwards\n"
+              << "      --resume    Checkpoint finished points in <output>.partial and skip them when restarted\n"
               << "      --reuse-shift  -f J / -f U: the chemical potential only shifts the spectrum; solve each row once\n";
 }
 
@@ -54,7 +55,7 @@ int main(int argc, char* argv[])
                                 {"type", required_argument, nullptr, 't'},       {"iterations", required_argument, nullptr, 'i'},
                                 {"epsilon", required_argument, nullptr, 'e'},    {"gpus", required_argument, nullptr, 'g'},
                                 {"lattice", required_argument, nullptr, 'l'},    {"kernel", required_argument, nullptr, 'k'},
-                                {"output", required_argument, nullptr, 'o'},     {"concurrent", required_argument, nullptr, 'c'},     {"no-plot", no_argument, nullptr, 1000},         {"reuse-shift", no_argument, nullptr, 1001},
+                                {"output", required_argument, nullptr, 'o'},     {"concurrent", required_argument, nullptr, 'c'},     {"no-plot", no_argument, nullptr, 1000},         {"reuse-shift", no_argument, nullptr, 1001},      {"resume", no_argument, nullptr, 1002},
                                 {"help", no_argument, nullptr, 'h'},             {nullptr, no_argument, nullptr, 0}};
     while (true) {
         const int o = getopt_long(argc, argv, short_opts, long_opts, nullptr);
@@ -85,6 +86,7 @@ int main(int argc, char* argv[])
             case 'c': opt.contexts_per_gpu = std::stoi(optarg); break;
             case 1000: plot = false; break;
             case 1001: opt.reuse_shift = true; break;
+            case 1002: opt.resume = true; break;
             case 'h':
             default: print_usage(); return 0;
         }

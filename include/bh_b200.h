@@ -41,7 +41,8 @@ enum { BH_OK = 0, BH_ERR_ARG = -1, BH_ERR_CUDA = -2, BH_ERR_STATE = -3, BH_ERR_N
 enum { BH_ORDER_LEX = 0, BH_ORDER_TAG_SORTED = 1, BH_ORDER_REF_SCATTER = 2 };
 enum { BH_TERM_J = 0, BH_TERM_U = 1, BH_TERM_MU = 2 };
 /* H.v kernels: stored CSR (K3) or matrix-free on-the-fly (K4) */
-enum { BH_HV_STORED = 0, BH_HV_MATRIX_FREE = 1, BH_HV_USER = 2 /* matrix loaded with bh_load_matrix */ };
+enum { BH_HV_STORED = 0, BH_HV_MATRIX_FREE = 1, BH_HV_USER = 2 /* matrix loaded with bh_load_matrix */,
+       BH_HV_HYBRID = 3 /* chains: first rows through the stored slices, the rest matrix-free, in one launch */ };
 
 /* ---- context ------------------------------------------------------------------------------- */
 int bh_ctx_create(int device, bh_ctx** ctx);

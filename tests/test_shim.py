@@ -148,3 +148,21 @@ def test_variable_n_api_against_reference():
                         [("outer", np.int32), ("inner", np.int32), ("val", np.float64)])
         for nm in ("outer", "inner", "val"):
             assert (r[nm] == G[f"maxham_{term}_4_1_3_{nm}"]).all(), (term, nm)
+
+
+def test_cli_checkpoint_resume():
+    # --resume: finished points go to phase.txt.partial; a second run recomputes nothing and writes the same file
+    with tempfile.TemporaryDirectory() as td:
+        args = [str(a) for a in CLI_RUNS["phase_m6_fJ.txt"]] + ["--resume", "--no-plot"]
+        p = subprocess.run([CLI] + args, cwd=td, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0
+        first = open(os.path.join(td, "phase.txt")).read()
+        part = open(os.path.join(td, "phase.txt.partial")).read().splitlines()
+        assert part[0].startswith("# m 6 n 6 fixed J") and len(part) == 1 + 16
+        # drop the last 5 checkpointed points: only those are recomputed
+        open(os.path.join(td, "phase.txt.partial"), "w").write("\n".join(part[:-5]) + "\n")
+        p = subprocess.run([CLI] + args, cwd=td, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0
+        assert open(os.path.join(td, "phase.txt")).read() == first
+        assert len(open(os.path.join(td, "phase.txt.partial")).read().splitlines()) == 1 + 16
+    assert first == open(os.path.join(GOLD, "phase_m6_fJ.txt")).read()

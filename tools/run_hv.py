@@ -18,7 +18,8 @@ ctx = pkg.Context(0); ctx.set_stream(stream.cuda_stream); ctx.setup(m, n, nbr)
 D = ctx.D
 x = torch.empty(D, dtype=torch.float64, device="cuda"); y = torch.empty(D, dtype=torch.float64, device="cuda")
 ctx.lcg_fill_dev(x.data_ptr(), D)
-for name, kid in (("stored", capi.HV_STORED), ("free", capi.HV_MATRIX_FREE)):
+ref = None
+for name, kid in (("stored", capi.HV_STORED), ("free", capi.HV_MATRIX_FREE), ("hybrid", capi.HV_HYBRID)):
     if which not in (name, "both"): continue
     for _ in range(3): ctx.hv_dev(1.0, 4.0, 1.0, x.data_ptr(), y.data_ptr(), kid)
     torch.cuda.synchronize()
@@ -28,4 +29,6 @@ for name, kid in (("stored", capi.HV_STORED), ("free", capi.HV_MATRIX_FREE)):
     b.record(stream); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
     ab = ctx.hv_algorithmic_bytes(kid)
-    print(f"{name}: D={D} nnzH={ctx.hamiltonian_nnz()} {ms*1e3:.1f} us/launch  algorithmic {ab/1e6:.1f} MB -> {ab/ms/1e6:.1f} GB/s", flush=True)
+    if ref is None: ref = y.clone()
+    err = float((y - ref).abs().max() / ref.abs().max())
+    print(f"{name}: maxrel vs first {err:.1e} D={D} nnzH={ctx.hamiltonian_nnz()} {ms*1e3:.1f} us/launch  algorithmic {ab/1e6:.1f} MB -> {ab/ms/1e6:.1f} GB/s", flush=True)
