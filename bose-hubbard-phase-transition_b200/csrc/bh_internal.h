@@ -58,7 +58,12 @@ struct bh_ctx {
     BhTables h_tab;
     BhTables* d_tab = nullptr;
     int max_row = 0;  // max entries per row of H (incl. diagonal)
-    int free_variant = 1;  // matrix-free H.v: 0 = fully unrolled site pairs, 1 = bond list + shared-memory prefixes (env BH_FREE_VARIANT)
+    // matrix-free H.v (env BH_FREE_VARIANT): 0 = fully unrolled site pairs, 1 = chain sweep / bond list per row,
+    // 2 = split (prefix x suffix) kernel for chains on an unpartitioned context (hv_split.cu), else as 1
+    int free_variant = 2;
+    void* split = nullptr;  // bh_split_state (hv_split.cu), built on first use
+    int split_G = 8;        // prefixes per warp (env BH_SPLIT_G: 4, 8, 12, 16)
+    int split_p = 0;        // prefix sites, 0 = m / 2 (env BH_SPLIT_P)
     int hv_variant = 2;  // stored H.v: 0 = CSR-stream, 1 = TMA-staged CSR-stream, 2 = SELL-32 (default; env BH_HV_VARIANT)
     int hv_stages = 3;   // ring depth of the TMA variant (env BH_HV_STAGES)
     int tile_cap = 0;    // entries per shared-memory stage of the TMA variant
@@ -162,6 +167,10 @@ struct BhEpilogue {
 };
 int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x_dev, double* y_dev,
                  const BhEpilogue& ep = BhEpilogue());
+// split matrix-free kernel for chains (hv_split.cu)
+bool bh_split_supported(const bh_ctx* ctx);
+int bh_launch_hv_split(bh_ctx* ctx, double cJ, double cU, double cmu, const double* x_dev, double* y_dev, const BhEpilogue& ep);
+void bh_split_release(bh_ctx* ctx);
 // rigorous (Gershgorin) bounds of the spectrum of H(cJ, cU, cmu); model contexts only
 int bh_spectrum_bounds(bh_ctx* ctx, double cJ, double cU, double cmu, double* lo, double* hi);
 int bh_dist_allreduce_max(bh_ctx* ctx, double* buf_dev, int64_t count);

@@ -60,6 +60,8 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     ctx->own_stream = true;
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
     if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
+    if (const char* v = getenv("BH_SPLIT_G")) ctx->split_G = atoi(v);
+    if (const char* v = getenv("BH_SPLIT_P")) ctx->split_p = atoi(v);
     if (const char* v = getenv("BH_HYBRID_FRAC")) ctx->hybrid_frac = std::min(1.0, std::max(0.0, atof(v)));
     if (const char* v = getenv("BH_HYBRID_BLOCKS")) ctx->hybrid_sell_blocks = std::min(7, std::max(1, atoi(v)));
     if (const char* v = getenv("BH_SELL_SIGMA")) ctx->sell_sigma = std::min(1024, std::max(32, atoi(v) / 32 * 32));
@@ -84,6 +86,7 @@ int bh_release_system(bh_ctx* ctx)
 {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    bh_split_release(ctx);
     free_dev(ctx->d_tab); ctx->d_tab = nullptr;
     free_dev(ctx->d_states); ctx->d_states = nullptr;
     free_dev(ctx->d_dU); ctx->d_dU = nullptr;

@@ -711,7 +711,11 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
             xin = ctx->d_xfull;
         }
         if (nloc > 0) {
-            if (ctx->free_variant == 1 && ctx->h_tab.chain) {
+            if (ctx->free_variant >= 2 && bh_split_supported(ctx)) {
+                BH_TRY(bh_launch_hv_split(ctx, cJ, cU, cmu, xin, y, ep));
+                fused = true;
+                ctx->launches--;  // counted by bh_launch_hv_split
+            } else if (ctx->free_variant >= 1 && ctx->h_tab.chain) {
                 hv_free_fn_t fn = (ctx->h_tab.chain == 2) ? hv_chain_kernel<true>(ctx->m) : hv_chain_kernel<false>(ctx->m);
                 int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
                 fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y, ep);
