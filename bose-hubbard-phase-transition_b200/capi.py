@@ -23,7 +23,7 @@ SYMBOLS = [
     "bh_neighbours_chain", "bh_neighbours_rect", "bh_dimension", "bh_setup", "bh_basis", "bh_rank",
     "bh_term_nnz", "bh_term_csc", "bh_hamiltonian_nnz", "bh_hamiltonian_csc", "bh_hv", "bh_hv_dev", "bh_eigs",
     "bh_spdm", "bh_gap_ratios", "bh_condensate_fraction", "bh_coherence", "bh_point", "bh_points",
-    "bh_lcg_fill_dev", "bh_hv_algorithmic_bytes", "bh_load_matrix",
+    "bh_lcg_fill_dev", "bh_hv_algorithmic_bytes", "bh_load_matrix", "bh_ctx_set_batch",
     "bh_dist_unique_id", "bh_dist_init", "bh_dist_finalize", "bh_setup_partitioned", "bh_partition",
 ]
 
@@ -82,6 +82,7 @@ def load():
     L.bh_coherence.argtypes = [C.c_int, vp, dp]
     L.bh_point.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, C.POINTER(EigsInfo)]
     L.bh_points.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
+    L.bh_ctx_set_batch.argtypes = [vp, C.c_int]
     L.bh_dist_unique_id.argtypes = [vp]
     L.bh_dist_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.bh_dist_finalize.argtypes = [vp]
@@ -177,6 +178,11 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.L.bh_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_batch(self, batch):
+        """bh_points solves `batch` (1..4) grid points in lockstep, sharing their H.v launches."""
+        self._check(self.L.bh_ctx_set_batch(self.h, int(batch)))
+        return self
 
     def launch_count(self):
         return self.L.bh_ctx_launch_count(self.h)

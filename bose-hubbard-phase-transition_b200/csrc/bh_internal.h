@@ -43,6 +43,13 @@ struct bh_ctx {
     int64_t launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;  // bytes copied across PCIe by this context
 
+    // lockstep batching of grid points (batch.cu): bh_points solves `batch` points together, sharing their H.v launches
+    int batch = 1;                       // env BH_BATCH / bh_ctx_set_batch (1 = off, 2..4)
+    struct bh_batch_hub* hub = nullptr;  // parent side: scheduling state + interleaved buffers
+    std::vector<bh_ctx*> children;       // parent side: one workspace-owning context per lockstep solve
+    bh_ctx* parent = nullptr;            // child side
+    int fiber = -1;                      // child side: index inside the batch
+
     // system
     bool user_matrix = false;  // true after bh_load_matrix: no Fock basis, only the SELL copy of the given matrix
     int m = 0, n = 0;
@@ -60,9 +67,11 @@ struct bh_ctx {
     int max_row = 0;  // max entries per row of H (incl. diagonal)
     // matrix-free H.v (env BH_FREE_VARIANT): 0 = fully unrolled site pairs, 1 = chain sweep / bond list per row,
     // 2 = split (prefix x suffix) kernel for chains on an unpartitioned context (hv_split.cu), else as 1
-    int free_variant = 2;
+    int free_variant = 1;
     void* split = nullptr;  // bh_split_state (hv_split.cu), built on first use
-    int split_G = 8;        // prefixes per warp (env BH_SPLIT_G: 4, 8, 12, 16)
+    int split_G = 4;        // prefixes per warp (env BH_SPLIT_G)
+    int split_UJ = 2;       // hops in flight together per prefix (env BH_SPLIT_UJ)
+    int split_nx = 8;       // warps of a CTA along the suffix direction (env BH_SPLIT_NX: 1, 2, 4, 8)
     int split_p = 0;        // prefix sites, 0 = m / 2 (env BH_SPLIT_P)
     int hv_variant = 2;  // stored H.v: 0 = CSR-stream, 1 = TMA-staged CSR-stream, 2 = SELL-32 (default; env BH_HV_VARIANT)
     int hv_stages = 3;   // ring depth of the TMA variant (env BH_HV_STAGES)
@@ -155,6 +164,14 @@ int bh_fail(bh_ctx* ctx, int code, const std::string& msg);
 
 // ---- internal entry points (defined across the .cu files) ----
 int bh_release_system(bh_ctx* ctx);
+void bh_release_workspace(bh_ctx* ctx);  // Krylov workspace, staging, scratch (everything a lockstep child owns)
+// lockstep batching (batch.cu)
+bool bh_batch_supported(const bh_ctx* ctx, int kernel);
+int bh_points_lockstep(bh_ctx* ctx, int nb, const double* cJ, const double* cU, const double* cmu, int nb_eigen, int kernel,
+                       double* out3, bh_eigs_info* infos);
+int bh_batch_filter(bh_ctx* child, const double* x, double* y, double c, double e, double cJ, double cU, double cmu, int d,
+                    bool* handled);
+void bh_batch_release(bh_ctx* ctx);
 int bh_build_basis(bh_ctx* ctx);          // K1: states, dU
 int bh_build_hamiltonian(bh_ctx* ctx);    // K2: pattern, J values
 int bh_ensure_orderings(bh_ctx* ctx);     // tags, radix sort, permutations

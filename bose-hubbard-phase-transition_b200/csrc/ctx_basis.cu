@@ -60,8 +60,11 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     ctx->own_stream = true;
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
     if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
+    if (const char* v = getenv("BH_BATCH")) ctx->batch = std::min(4, std::max(1, atoi(v)));
     if (const char* v = getenv("BH_SPLIT_G")) ctx->split_G = atoi(v);
     if (const char* v = getenv("BH_SPLIT_P")) ctx->split_p = atoi(v);
+    if (const char* v = getenv("BH_SPLIT_UJ")) ctx->split_UJ = atoi(v);
+    if (const char* v = getenv("BH_SPLIT_NX")) ctx->split_nx = atoi(v);
     if (const char* v = getenv("BH_HYBRID_FRAC")) ctx->hybrid_frac = std::min(1.0, std::max(0.0, atof(v)));
     if (const char* v = getenv("BH_HYBRID_BLOCKS")) ctx->hybrid_sell_blocks = std::min(7, std::max(1, atoi(v)));
     if (const char* v = getenv("BH_SELL_SIGMA")) ctx->sell_sigma = std::min(1024, std::max(32, atoi(v) / 32 * 32));
@@ -82,10 +85,31 @@ static void free_dev(void* p)
     if (p) cudaFree(p);
 }
 
+void bh_release_workspace(bh_ctx* ctx)
+{
+    free_dev(ctx->d_V); ctx->d_V = nullptr;
+    free_dev(ctx->d_w); ctx->d_w = nullptr;
+    free_dev(ctx->d_f); ctx->d_f = nullptr;
+    free_dev(ctx->d_scal); ctx->d_scal = nullptr;
+    free_dev(ctx->d_part); ctx->d_part = nullptr;
+    free_dev(ctx->d_counter); ctx->d_counter = nullptr;
+    free_dev(ctx->d_small); ctx->d_small = nullptr;
+    for (int q = 0; q < 3; ++q) { free_dev(ctx->d_cheb[q]); ctx->d_cheb[q] = nullptr; }
+    free_dev(ctx->d_spdm_scratch); ctx->d_spdm_scratch = nullptr;
+    ctx->spdm_scratch_bytes = 0;
+    free_dev(ctx->d_x); ctx->d_x = nullptr;
+    free_dev(ctx->d_y); ctx->d_y = nullptr;
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    ctx->h_pinned = nullptr;
+    ctx->h_pinned_bytes = 0;
+    ctx->ws_ncv = 0;
+}
+
 int bh_release_system(bh_ctx* ctx)
 {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    bh_batch_release(ctx);  // lockstep children alias the arrays freed below
     bh_split_release(ctx);
     free_dev(ctx->d_tab); ctx->d_tab = nullptr;
     free_dev(ctx->d_states); ctx->d_states = nullptr;
@@ -107,22 +131,7 @@ int bh_release_system(bh_ctx* ctx)
     free_dev(ctx->d_tags); ctx->d_tags = nullptr;
     free_dev(ctx->d_perm_tag); ctx->d_perm_tag = nullptr;
     free_dev(ctx->d_inv_tag); ctx->d_inv_tag = nullptr;
-    free_dev(ctx->d_V); ctx->d_V = nullptr;
-    free_dev(ctx->d_w); ctx->d_w = nullptr;
-    free_dev(ctx->d_f); ctx->d_f = nullptr;
-    free_dev(ctx->d_scal); ctx->d_scal = nullptr;
-    free_dev(ctx->d_part); ctx->d_part = nullptr;
-    free_dev(ctx->d_counter); ctx->d_counter = nullptr;
-    free_dev(ctx->d_small); ctx->d_small = nullptr;
-    for (int q = 0; q < 3; ++q) { free_dev(ctx->d_cheb[q]); ctx->d_cheb[q] = nullptr; }
-    free_dev(ctx->d_spdm_scratch); ctx->d_spdm_scratch = nullptr;
-    ctx->spdm_scratch_bytes = 0;
-    free_dev(ctx->d_x); ctx->d_x = nullptr;
-    free_dev(ctx->d_y); ctx->d_y = nullptr;
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    ctx->h_pinned = nullptr;
-    ctx->h_pinned_bytes = 0;
-    ctx->ws_ncv = 0;
+    bh_release_workspace(ctx);
     ctx->tile_cap = 0;
     ctx->hv_smem_configured = 0;
     ctx->valH_valid = false;
@@ -159,6 +168,14 @@ extern "C" int bh_ctx_set_stream(bh_ctx* ctx, void* cuda_stream)
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->own_stream = false;
     ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return BH_OK;
+}
+
+extern "C" int bh_ctx_set_batch(bh_ctx* ctx, int batch)
+{
+    if (!ctx) return BH_ERR_ARG;
+    if (batch < 1 || batch > 4) return bh_fail(ctx, BH_ERR_ARG, "bh_ctx_set_batch: batch must be 1..4");
+    ctx->batch = batch;
     return BH_OK;
 }
 

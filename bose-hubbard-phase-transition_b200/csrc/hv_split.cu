@@ -26,6 +26,7 @@
 struct SplitDev {
     int n, closed, WP, WS, rec_bytes;
     uint32_t nitems;
+    int ablate;  // experiments only (env BH_SPLIT_ABLATE): 1 skip suffix bonds, 2 skip prefix bonds, 4 skip cut/periodic bonds
     const unsigned char* prec;
     const uint32_t* sinfo;
     const uint4* scross;
@@ -35,7 +36,7 @@ struct SplitDev {
 
 struct bh_split_state {
     SplitDev dev;
-    int G = 0, p = 0;
+    int G = 0, UJ = 0, p = 0;
     size_t smem = 0;
     size_t table_bytes = 0;
 };
@@ -51,7 +52,9 @@ __device__ __forceinline__ double ldx(const double* __restrict__ x, uint32_t b)
 }
 
 // One warp: 32 suffixes (lane) x up to G prefixes.  FULL = all G prefixes present (no per-prefix guards in the loops).
-template <int G, bool FULL>
+// UJ hops are processed together so that UJ * G independent gathers are in flight per lane (the kernel is latency-bound
+// otherwise: ncu long-scoreboard stalls on the first use of every loaded value).
+template <int G, int UJ, bool FULL>
 __device__ __forceinline__ void split_warp(const SplitDev& T, const double* sq, const unsigned char* recb, int gcount, int R,
                                            uint32_t nS, uint32_t nSpad, uint32_t sbase, uint32_t S, double cJ, double cU,
                                            double cmu, const double* __restrict__ x, double* __restrict__ y,
@@ -59,9 +62,14 @@ __device__ __forceinline__ void split_warp(const SplitDev& T, const double* sq, 
 {
     const bool valid = S < nS;
     const uint32_t Sb = (valid ? S : nS - 1) * 8u;
+    const uint32_t* nb = T.snbr + (size_t)sbase * T.WS + S;
+    const int WS = T.WS;
+    // first block of suffix-hop words, issued before anything depends on them
+    uint32_t vcur[UJ];
+#pragma unroll
+    for (int u = 0; u < UJ; ++u) vcur[u] = (u < WS) ? __ldg(nb + (size_t)u * nSpad) : 0u;
     const uint32_t si = __ldg(T.sinfo + sbase + S);
     const uint4 cr = __ldg(T.scross + sbase + S);
-    const int np = si & 15, nl = (si >> 4) & 15, scnt = (si >> 8) & 255, dUs = si >> 16;
     const uint32_t rb = T.rec_bytes;
 
     uint32_t ob[G];  // byte offset of row P_g
@@ -80,32 +88,54 @@ __device__ __forceinline__ void split_warp(const SplitDev& T, const double* sq, 
         }
     }
 
-    // ---- suffix bonds: 1 (x) B ----
-    {
-        const uint32_t* nb = T.snbr + (size_t)sbase * T.WS + S;
-        const int smax = __reduce_max_sync(0xffffffffu, scnt);
-#pragma unroll 2
-        for (int j = 0; j < smax; ++j) {
-            const uint32_t v = __ldg(nb + (size_t)j * nSpad);
-            const double a = sq[v >> 24];
-            const uint32_t ib = (v & 0xffffffu) * 8u;
-#pragma unroll
-            for (int g = 0; g < G; ++g)
-                if (FULL || g < gcount) acc[g] = fma(a, ldx(x, ob[g] + ib), acc[g]);
-        }
-    }
-
     // ---- prefix bonds: A (x) 1 (padding entries point at the own row with amplitude 0) ----
     {
         const unsigned char* nbp = recb + sizeof(SplitPrefixHdr);
-        for (int j = 0; j < pmax; ++j) {
+        if (!(T.ablate & 2))
+        for (int j0 = 0; j0 < pmax; j0 += UJ) {
+            double val[UJ][G], a[UJ][G];
 #pragma unroll
-            for (int g = 0; g < G; ++g)
-                if (FULL || g < gcount) {
-                    const uint4 e = *reinterpret_cast<const uint4*>(nbp + g * rb + j * sizeof(SplitNbr));
-                    const double a = __hiloint2double((int)e.w, (int)e.z);
-                    acc[g] = fma(a, ldx(x, e.x + Sb), acc[g]);  // e.x = byte offset of row P'
+            for (int u = 0; u < UJ; ++u)
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    val[u][g] = 0.0;
+                    a[u][g] = 0.0;
+                    if ((FULL || g < gcount) && j0 + u < pmax) {
+                        const uint4 e = *reinterpret_cast<const uint4*>(nbp + g * rb + (j0 + u) * sizeof(SplitNbr));
+                        a[u][g] = __hiloint2double((int)e.w, (int)e.z);
+                        val[u][g] = ldx(x, e.x + Sb);  // e.x = byte offset of row P'
+                    }
                 }
+#pragma unroll
+            for (int u = 0; u < UJ; ++u)
+#pragma unroll
+                for (int g = 0; g < G; ++g) acc[g] = fma(a[u][g], val[u][g], acc[g]);
+        }
+    }
+
+    const int np = si & 15, nl = (si >> 4) & 15, scnt = (si >> 8) & 255, dUs = si >> 16;
+    // ---- suffix bonds: 1 (x) B ----
+    {
+        const int smax = (T.ablate & 1) ? 0 : __reduce_max_sync(0xffffffffu, scnt);
+        for (int j0 = 0; j0 < smax; j0 += UJ) {
+            uint32_t vnext[UJ];
+#pragma unroll
+            for (int u = 0; u < UJ; ++u) vnext[u] = (j0 + UJ + u < smax) ? __ldg(nb + (size_t)(j0 + UJ + u) * nSpad) : 0u;
+            double val[UJ][G], a[UJ];
+#pragma unroll
+            for (int u = 0; u < UJ; ++u) {
+                const bool on = j0 + u < smax;
+                a[u] = on ? sq[vcur[u] >> 24] : 0.0;
+                const uint32_t ib = (vcur[u] & 0xffffffu) * 8u;
+#pragma unroll
+                for (int g = 0; g < G; ++g) val[u][g] = ((FULL || g < gcount) && on) ? ldx(x, ob[g] + ib) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < UJ; ++u) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) acc[g] = fma(a[u], val[u][g], acc[g]);
+                vcur[u] = vnext[u];
+            }
         }
     }
 
@@ -113,33 +143,40 @@ __device__ __forceinline__ void split_warp(const SplitDev& T, const double* sq, 
     const double shift = __dmul_rn(-(double)T.n, cmu);
     const double twoJ = 2.0 * cJ;
     const uint32_t cx = cr.x * 8u, cy = cr.y * 8u, cz = cr.z * 8u, cw = cr.w * 8u;
+    double c0[G], c1[G], c2[G], c3[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-        if (FULL || g < gcount) {
+    for (int g = 0; g < G; ++g) {
+        c0[g] = c1[g] = c2[g] = c3[g] = 0.0;
+        if ((FULL || g < gcount) && !(T.ablate & 4)) {
             const SplitPrefixHdr* h = reinterpret_cast<const SplitPrefixHdr*>(recb + g * rb);
             const uint4 o = *reinterpret_cast<const uint4*>(h);  // off_cu, off_cd, off_wu, off_wd (byte offsets)
             const uint32_t info = h->info;
-            const int n0 = info & 15, nq = (info >> 4) & 15, dUp = info >> 16;
-            double a = acc[g];
+            const int n0 = info & 15, nq = (info >> 4) & 15;
             if (R >= 1) {
-                if (np) a = fma(sq[(nq + 1) * np], ldx(x, o.x + cx), a);               // boson moves p -> p-1
-                if (T.closed && nl) a = fma(sq[(n0 + 1) * nl], ldx(x, o.z + cz), a);  // boson moves m-1 -> 0
+                if (np) c0[g] = sq[(nq + 1) * np] * ldx(x, o.x + cx);               // boson moves p -> p-1
+                if (T.closed && nl) c2[g] = sq[(n0 + 1) * nl] * ldx(x, o.z + cz);  // boson moves m-1 -> 0
             }
-            if (nq) a = fma(sq[(np + 1) * nq], ldx(x, o.y + cy), a);                  // boson moves p-1 -> p
-            if (T.closed && n0) a = fma(sq[(nl + 1) * n0], ldx(x, o.w + cw), a);      // boson moves 0 -> m-1
-            if (valid) {
-                const size_t l = (size_t)(ob[g] >> 3) + S;
-                const double diag = __dadd_rn(__dmul_rn((double)(dUp + dUs), cU), shift);
-                double out = ep.s1 * (diag * xv[g] - twoJ * a);
-                if (ep.s2 != 0.0) out = fma(ep.s2, xv[g], out);
-                if (ep.z) out = fma(ep.s3, __ldcs(ep.z + l), out);
-                __stcs(y + l, out);
-            }
+            if (nq) c1[g] = sq[(np + 1) * nq] * ldx(x, o.y + cy);                  // boson moves p-1 -> p
+            if (T.closed && n0) c3[g] = sq[(nl + 1) * n0] * ldx(x, o.w + cw);      // boson moves 0 -> m-1
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+        if ((FULL || g < gcount) && valid) {
+            const SplitPrefixHdr* h = reinterpret_cast<const SplitPrefixHdr*>(recb + g * rb);
+            const int dUp = h->info >> 16;
+            const double a = acc[g] + ((c0[g] + c1[g]) + (c2[g] + c3[g]));
+            const size_t l = (size_t)(ob[g] >> 3) + S;
+            const double diag = __dadd_rn(__dmul_rn((double)(dUp + dUs), cU), shift);
+            double out = ep.s1 * (diag * xv[g] - twoJ * a);
+            if (ep.s2 != 0.0) out = fma(ep.s2, xv[g], out);
+            if (ep.z) out = fma(ep.s3, __ldcs(ep.z + l), out);
+            __stcs(y + l, out);
         }
 }
 
-template <int G>
-__global__ void __launch_bounds__(256, SPLIT_MINB)
+template <int G, int UJ, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_hv_split(const __grid_constant__ SplitDev T, const BhTables* __restrict__ gtab, double cJ, double cU, double cmu,
            const double* __restrict__ x, double* __restrict__ y, BhEpilogue ep)
 {
@@ -171,20 +208,26 @@ k_hv_split(const __grid_constant__ SplitDev T, const BhTables* __restrict__ gtab
     const uint32_t S = chunk * 32 + lane;
     const unsigned char* recb = reinterpret_cast<const unsigned char*>(s_rec) + (size_t)(wy * G) * T.rec_bytes;
     if (gcount == G)
-        split_warp<G, true>(T, sq, recb, gcount, R, nS, nSpad, sbase, S, cJ, cU, cmu, x, y, ep);
+        split_warp<G, UJ, true>(T, sq, recb, gcount, R, nS, nSpad, sbase, S, cJ, cU, cmu, x, y, ep);
     else
-        split_warp<G, false>(T, sq, recb, gcount, R, nS, nSpad, sbase, S, cJ, cU, cmu, x, y, ep);
+        split_warp<G, UJ, false>(T, sq, recb, gcount, R, nS, nSpad, sbase, S, cJ, cU, cmu, x, y, ep);
 }
 
 typedef void (*hv_split_fn)(const SplitDev, const BhTables*, double, double, double, const double*, double*, BhEpilogue);
 
-static hv_split_fn split_kernel(int G)
+static hv_split_fn split_kernel(int G, int UJ)
 {
-    switch (G) {
-        case 4: return k_hv_split<4>;
-        case 8: return k_hv_split<8>;
-        case 12: return k_hv_split<12>;
-        case 16: return k_hv_split<16>;
+    switch (G * 16 + UJ) {
+        case 2 * 16 + 2: return k_hv_split<2, 2, 5>;
+        case 2 * 16 + 4: return k_hv_split<2, 4, 4>;
+        case 2 * 16 + 6: return k_hv_split<2, 6, 4>;
+        case 4 * 16 + 1: return k_hv_split<4, 1, 3>;
+        case 4 * 16 + 2: return k_hv_split<4, 2, 3>;
+        case 4 * 16 + 3: return k_hv_split<4, 3, 3>;
+        case 4 * 16 + 4: return k_hv_split<4, 4, 2>;
+        case 8 * 16 + 1: return k_hv_split<8, 1, 2>;
+        case 8 * 16 + 2: return k_hv_split<8, 2, 2>;
+        case 16 * 16 + 1: return k_hv_split<16, 1, 1>;
     }
     return nullptr;
 }
@@ -211,12 +254,13 @@ static int ensure_tables(bh_ctx* ctx)
 {
     if (ctx->split) return BH_OK;
     int G = ctx->split_G;
-    if (!split_kernel(G)) return bh_fail(ctx, BH_ERR_ARG, "BH_SPLIT_G must be 4, 8, 12 or 16");
+    const int UJ = ctx->split_UJ;
+    if (!split_kernel(G, UJ)) return bh_fail(ctx, BH_ERR_ARG, "unsupported BH_SPLIT_G / BH_SPLIT_UJ combination");
     int p = ctx->split_p > 0 ? ctx->split_p : ctx->m / 2;
     p = std::min(std::max(p, 1), ctx->m - 1);
     SplitTables T;
     try {
-        bh_split_build(ctx->m, ctx->n, p, G, ctx->h_tab.chain == 2, &ctx->h_tab.f[0][0], BH_MAX_BOSONS + 3, T);
+        bh_split_build(ctx->m, ctx->n, p, G, ctx->h_tab.chain == 2, &ctx->h_tab.f[0][0], BH_MAX_BOSONS + 3, T, ctx->split_nx);
     } catch (const std::exception& e) {
         return bh_fail(ctx, BH_ERR_STATE, std::string("split H.v tables: ") + e.what());
     }
@@ -230,9 +274,11 @@ static int ensure_tables(bh_ctx* ctx)
     }
     bh_split_state* st = new bh_split_state();
     st->G = G;
+    st->UJ = UJ;
     st->p = p;
     SplitDev& d = st->dev;
     std::memset(&d, 0, sizeof(d));
+    d.ablate = getenv("BH_SPLIT_ABLATE") ? atoi(getenv("BH_SPLIT_ABLATE")) : 0;
     d.n = T.n; d.closed = T.closed; d.WP = T.WP; d.WS = T.WS; d.rec_bytes = T.rec_bytes; d.nitems = T.nitems;
     std::memcpy(d.sec, T.sec, sizeof(d.sec));
     ctx->split = st;  // from here bh_split_release frees whatever was allocated
@@ -252,7 +298,7 @@ static int ensure_tables(bh_ctx* ctx)
     st->smem = (size_t)8 * G * T.rec_bytes;
     if (st->smem > 200 * 1024) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "split H.v: prefix records do not fit in shared memory");
     if (st->smem > 48 * 1024)
-        BH_CUDA(ctx, cudaFuncSetAttribute(split_kernel(G), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem));
+        BH_CUDA(ctx, cudaFuncSetAttribute(split_kernel(G, UJ), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem));
     if (getenv("BH_SPLIT_VERBOSE"))
         fprintf(stderr, "[bh] split H.v: m=%d n=%d p=%d G=%d items=%u prefixes=%u suffixes(padded)=%u tables=%.1f MB smem=%zu\n", ctx->m,
                 ctx->n, p, G, T.nitems, T.NP, T.NSpad, st->table_bytes / 1e6, st->smem);
@@ -264,7 +310,7 @@ int bh_launch_hv_split(bh_ctx* ctx, double cJ, double cU, double cmu, const doub
     if (!bh_split_supported(ctx)) return bh_fail(ctx, BH_ERR_STATE, "split H.v needs a chain on an unpartitioned context");
     BH_TRY(ensure_tables(ctx));
     bh_split_state* st = static_cast<bh_split_state*>(ctx->split);
-    split_kernel(st->G)<<<st->dev.nitems, 256, st->smem, ctx->stream>>>(st->dev, ctx->d_tab, cJ, cU, cmu, x, y, ep);
+    split_kernel(st->G, st->UJ)<<<st->dev.nitems, 256, st->smem, ctx->stream>>>(st->dev, ctx->d_tab, cJ, cU, cmu, x, y, ep);
     BH_LAUNCHED(ctx);
     return BH_OK;
 }

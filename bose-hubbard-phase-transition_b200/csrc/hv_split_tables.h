@@ -90,10 +90,13 @@ inline void enumerate(int sites, int total, std::vector<int>& cur, std::vector<s
 
 // f[q][R] is BhTables::f (ctx_basis.cu): f[q][R] = [R > 0] C(R - 1 + m - 1 - q, m - 1 - q), row stride fstride ints.
 // Builds the tables for the chain of m sites (closed: periodic bond listed), n bosons, p prefix sites, G prefixes per warp.
-inline void bh_split_build(int m, int n, int p, int G, bool closed, const int* f, int fstride, SplitTables& T)
+// max_nx (1, 2, 4, 8): warps of a CTA laid along the suffix direction for long rows; the other 8 / nx cover prefix groups.
+inline void bh_split_build(int m, int n, int p, int G, bool closed, const int* f, int fstride, SplitTables& T, int max_nx = 8)
 {
     using namespace bh_split_detail;
-    if (m < 3 || p < 1 || p > m - 1 || n < 1 || n + 1 > BH_SPLIT_MAX_SECTORS || G < 1) throw std::invalid_argument("bh_split_build");
+    if (m < 3 || p < 1 || p > m - 1 || n < 1 || n + 1 > BH_SPLIT_MAX_SECTORS || G < 1 ||
+        (max_nx != 1 && max_nx != 2 && max_nx != 4 && max_nx != 8))
+        throw std::invalid_argument("bh_split_build");
     const int s = m - p;
     T = SplitTables();
     T.m = m; T.n = n; T.p = p; T.s = s; T.G = G; T.closed = closed ? 1 : 0;
@@ -137,6 +140,7 @@ inline void bh_split_build(int m, int n, int p, int G, bool closed, const int* f
         sc.sbase = sbase;
         const uint32_t nchunks = sc.nSpad / 32;
         sc.nx = nchunks >= 5 ? 8 : nchunks >= 3 ? 4 : nchunks;
+        while ((int)sc.nx > max_nx) sc.nx /= 2;
         sc.ny = 8 / sc.nx;
         sc.ncb = (nchunks + sc.nx - 1) / sc.nx;
         const uint32_t ngroups = (sc.nP + G - 1) / G;

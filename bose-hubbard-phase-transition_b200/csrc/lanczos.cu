@@ -916,6 +916,14 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
         }
     // ---- stage 2 ----
     LanczosOp cheb = [&](const double* x, double* y) {
+        if (ctx->parent && ctx->parent->hub) {  // lockstep solve (batch.cu): the filters of all live solves share their launches
+            bool handled = false;
+            BH_TRY(bh_batch_filter(ctx, x, y, c, e, cJ, cU, cmu, d, &handled));
+            if (handled) {
+                hv_count += d;
+                return (int)BH_OK;
+            }
+        }
         const double* tkm2 = x;        // T_{k-2}
         const double* tkm1 = nullptr;  // T_{k-1}
         for (int k = 1; k <= d; ++k) {

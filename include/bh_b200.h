@@ -128,6 +128,11 @@ int bh_point(bh_ctx* ctx, double cJ, double cU, double cmu, int nb_eigen, int ke
 /* A list of grid points on this context (the shard of one GPU): cJ/cU/cmu[npoints] -> out3[3*npoints]. */
 int bh_points(bh_ctx* ctx, const double* cJ, const double* cU, const double* cmu, int64_t npoints, int nb_eigen,
               int kernel, double* out3, bh_eigs_info* infos /* may be NULL */);
+/* Lockstep batching of bh_points (the independent iterations of the reference's `omp parallel for` over grid points,
+ * src/analysis.cpp:302): with batch = 2..4, groups of that many points are solved together and share their H.v
+ * launches (closed chains, kernel = BH_HV_MATRIX_FREE; anything else falls back to one point at a time).
+ * Results are the same point by point.  Default 1, or the environment variable BH_BATCH. */
+int bh_ctx_set_batch(bh_ctx* ctx, int batch);
 
 /* ---- one large eigensolve row-partitioned over several GPUs (BASELINE.json config 5) ---------------------
  * One process (or thread) per GPU.  Rank 0 creates a 128-byte NCCL id (bh_dist_unique_id) and hands it to the

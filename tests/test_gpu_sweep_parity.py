@@ -65,3 +65,22 @@ def test_j_zero_breakdown_recovery(pkg, ctx_factory, m, n):
         got = np.sort(ctx.eigs(0.0, 3.0, 0.5, nev=20, kernel=kernel)["evals"])
         assert abs(got[0] - levels[0]) <= 1e-9 * abs(levels[0])
         assert all(np.abs(levels - v).min() <= 1e-9 * abs(levels[0]) for v in got)
+
+
+@pytest.mark.parametrize("m,n", [(8, 8), (9, 7)])
+def test_lockstep_batches_equal_single_points(pkg, m, n):
+    """bh_points with batch = 2..4 (csrc/batch.cu: the Chebyshev filters of the batched points share their H.v launches)
+    returns, point by point, what one-at-a-time solves return; odd counts exercise the pair + single path."""
+    cU = np.array([1.0, 4.0, 2.5, 9.0, 6.0, 3.0, 12.0])
+    cJ = np.ones_like(cU)
+    cmu = np.array([0.0, 1.0, 2.0, 0.5, 0.0, 3.0, 1.0])
+    ctx = pkg.Context(0).setup(m, n)
+    ref3, refinfo = ctx.points(cJ, cU, cmu, kernel=pkg.capi.HV_MATRIX_FREE)
+    for batch in (2, 3, 4):
+        ctx.set_batch(batch)
+        for npts in (2, 3, 4, 5, 7):
+            out3, infos = ctx.points(cJ[:npts], cU[:npts], cmu[:npts], kernel=pkg.capi.HV_MATRIX_FREE)
+            assert np.allclose(out3, ref3[:npts], rtol=1e-9, atol=1e-12), (batch, npts, out3 - ref3[:npts])
+            assert [i["nmatvec"] for i in infos] == [i["nmatvec"] for i in refinfo[:npts]], (batch, npts)
+    ctx.set_batch(1)
+    ctx.close()

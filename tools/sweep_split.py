@@ -7,8 +7,8 @@ import torch
 import __graft_entry__ as g
 pkg = g.load_package(); capi = pkg.capi
 m, n, reps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-cuts = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [m // 2]
-groups = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [4, 8, 16]
+# configurations "p:G:UJ:NX" (cut position, prefixes per warp, hops in flight, warps along the suffix direction)
+configs = sys.argv[4].split(",") if len(sys.argv) > 4 else [f"{m // 2}:4:2:8"]
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 x = y = ref = None
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -16,7 +16,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 def run(label, env, cold=False):
     global x, y, ref
-    for k in ("BH_FREE_VARIANT", "BH_SPLIT_P", "BH_SPLIT_G"):
+    for k in ("BH_FREE_VARIANT", "BH_SPLIT_P", "BH_SPLIT_G", "BH_SPLIT_UJ", "BH_SPLIT_NX"):
         os.environ.pop(k, None)
     os.environ.update(env)
     ctx = pkg.Context(0); ctx.set_stream(stream.cuda_stream); ctx.setup(m, n)
@@ -47,6 +47,6 @@ def run(label, env, cold=False):
 
 
 run("chain kernel", {"BH_FREE_VARIANT": "1"})
-for p in cuts:
-    for G in groups:
-        run(f"split p={p} G={G}", {"BH_FREE_VARIANT": "2", "BH_SPLIT_P": str(p), "BH_SPLIT_G": str(G)})
+for c in configs:
+    p, G, UJ, NX = c.split(":")
+    run(f"split p={p} G={G} UJ={UJ} NX={NX}", {"BH_FREE_VARIANT": "2", "BH_SPLIT_P": p, "BH_SPLIT_G": G, "BH_SPLIT_UJ": UJ, "BH_SPLIT_NX": NX})
