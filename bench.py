@@ -6,7 +6,8 @@
 Workload (config 3 of BASELINE.json, SURVEY.md section 8d "C3"): closed chain m = 12 sites, n = 12 bosons
 (D = 1 352 078, nnz(H) = 18 282 446), the 32 x 32 grid of `-J 1 -U 0 -u 0 -r 31 -s 1 -f J`
 (J-coefficient 1, U-coefficient 1..32, mu 0..31).  A step = one batch of P grid points per GPU (eigensolve for
-the 20 lowest levels + gap ratio + SPDM + condensate fraction + coherence); every rank gets the same U values (a fixed
+the 20 lowest levels + gap ratio + SPDM + condensate fraction + coherence; the points of a batch are solved in lockstep and
+share their H.v launches, --batch, results identical point by point); every rank gets the same U values (a fixed
 pseudo-random order over the grid's 32) at different mu; per-GPU work is fixed as N grows (weak scaling, no data-path
 collective).
 
@@ -156,6 +157,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points-per-step", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=2,
+                    help="grid points solved in lockstep per GPU (bh_ctx_set_batch): their Chebyshev-filter H.v launches are shared")
     ap.add_argument("--kernel", default="free", choices=["stored", "free"],
                     help="H.v kernel of the eigensolver: matrix-free (chain-specialised, faster at m=n=12) or stored SELL-32")
     ap.add_argument("--hv-reps", type=int, default=50)
@@ -212,6 +215,7 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()
     ctx.setup(m, n)
+    ctx.set_batch(args.batch)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
 
@@ -252,6 +256,7 @@ def main():
     w0 = time.perf_counter()
     ctx2 = pkg.Context(local)
     ctx2.setup(m, n)
+    ctx2.set_batch(args.batch)
     for s in range(W, W + K):
         ctx2.points(*step_points(s), kernel=kernel)
     torch.cuda.synchronize()
@@ -356,7 +361,7 @@ def main():
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "C3: closed chain m=12 n=12 (D=1352078, nnz(H)=18282446), 32x32 grid of -J 1 -U 0 -u 0 -r 31 -s 1 -f J",
-                   "m": m, "n": n, "points_per_gpu_per_step": P, "nev": 20, "ncv": 41, "tol": 1e-10, "hv_kernel": args.kernel,
+                   "m": m, "n": n, "points_per_gpu_per_step": P, "nev": 20, "ncv": 41, "tol": 1e-10, "hv_kernel": args.kernel, "lockstep_batch": args.batch,
                    "solver": "thick-restart Lanczos on a degree-%s Chebyshev filter of H + Rayleigh-Ritz of H" % os.environ.get("BH_CHEB_DEGREE", "8"),
                    "l2": "inputs larger than L2 (Krylov basis 454 MB per point; stored H 433 MB for the roofline kernel)",
                    "mean_matvecs_per_point": int(np.mean(matvecs)) if matvecs else None, "setup_seconds": setup_s},

@@ -77,6 +77,7 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
     std::vector<bh_ctx*> ctxs(nworkers, nullptr);
     for (int d = 0; d < nworkers; ++d) {
         if (bh_ctx_create(d % ngpu, &ctxs[d]) != BH_OK) throw std::runtime_error(bh_last_error(nullptr));
+        bh_ctx_set_batch(ctxs[d], std::max(1, std::min(4, opt.batch)));
         if (bh_setup(ctxs[d], m, n, nbr_ptr.data(), nbr_idx.data()) != BH_OK) {
             std::string msg = bh_last_error(ctxs[d]);
             for (bh_ctx* c : ctxs) bh_ctx_destroy(c);
@@ -125,15 +126,15 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
         std::atomic<int> next(0), done(0);
         auto worker = [&](int d) {
             try {
+                const int B = std::max(1, std::min(4, opt.batch));
                 for (;;) {
-                    const int t = next.fetch_add(1);
-                    if (t >= ntasks) break;
-                    const int i = shift_rows ? t : t / g.num2, j = shift_rows ? 0 : t % g.num2;
-                    const double p1 = g.p1_min + i * g.step1;
-                    const double p2 = g.p2_min + j * g.step2;
-                    double cJ, cU, cmu, out3[3];
-                    coefficients(g, p1, p2, cJ, cU, cmu);
-                    {
+                    // up to B tasks per call: bh_points solves them in lockstep (shared H.v launches, same results)
+                    int ts[4], nt = 0;
+                    double cJ[4], cU[4], cmu[4], p1s[4], out3[12];
+                    while (nt < B) {
+                        const int t = next.fetch_add(1);
+                        if (t >= ntasks) break;
+                        const int i = shift_rows ? t : t / g.num2, j = shift_rows ? 0 : t % g.num2;
                         // resume: every output row this task would produce is already there
                         bool all = opt.resume;
                         for (int jj = j; all && jj < (shift_rows ? g.num2 : j + 1); ++jj) {
@@ -145,20 +146,30 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
                             done += shift_rows ? g.num2 : 1;
                             continue;
                         }
+                        p1s[nt] = g.p1_min + i * g.step1;
+                        coefficients(g, p1s[nt], g.p2_min + j * g.step2, cJ[nt], cU[nt], cmu[nt]);
+                        ts[nt++] = t;
                     }
-                    const int rc = bh_point(ctxs[d], cJ, cU, cmu, nb_eigen, opt.kernel, out3, nullptr, nullptr, nullptr);
+                    if (nt == 0) break;
+                    const int rc = nt == 1 ? bh_point(ctxs[d], cJ[0], cU[0], cmu[0], nb_eigen, opt.kernel, out3, nullptr, nullptr, nullptr)
+                                           : bh_points(ctxs[d], cJ, cU, cmu, nt, nb_eigen, opt.kernel, out3, nullptr);
                     if (rc == BH_ERR_ARG) throw std::invalid_argument(bh_last_error(ctxs[d]));
                     if (rc != BH_OK) throw std::runtime_error(bh_last_error(ctxs[d]));
                     std::lock_guard<std::mutex> lk(mtx);
-                    for (int jj = j; jj < (shift_rows ? g.num2 : j + 1); ++jj) {
-                        const int index = i * g.num1 + jj;  // src/analysis.cpp:341 (sic)
-                        if (index >= 0 && index < total) {
-                            res[index] = Analysis::SweepPoint{p1, g.p2_min + jj * g.step2, out3[0], out3[1], out3[2]};
-                            if (opt.resume)
-                                partial << index << " " << res[index].param1 << " " << res[index].param2 << " " << out3[0] << " " << out3[1]
-                                        << " " << out3[2] << std::endl;
+                    for (int q = 0; q < nt; ++q) {
+                        const int t = ts[q];
+                        const int i = shift_rows ? t : t / g.num2, j = shift_rows ? 0 : t % g.num2;
+                        const double* o3 = out3 + 3 * q;
+                        for (int jj = j; jj < (shift_rows ? g.num2 : j + 1); ++jj) {
+                            const int index = i * g.num1 + jj;  // src/analysis.cpp:341 (sic)
+                            if (index >= 0 && index < total) {
+                                res[index] = Analysis::SweepPoint{p1s[q], g.p2_min + jj * g.step2, o3[0], o3[1], o3[2]};
+                                if (opt.resume)
+                                    partial << index << " " << res[index].param1 << " " << res[index].param2 << " " << o3[0] << " " << o3[1]
+                                            << " " << o3[2] << std::endl;
+                            }
+                            ++done;
                         }
-                        ++done;
                     }
                     const int c = done.load();
                     if (opt.progress) {

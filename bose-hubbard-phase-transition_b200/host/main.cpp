@@ -36,6 +36,7 @@ static void print_usage()
               << "  -c, --concurrent Grid points solved concurrently per GPU (default 1)\n"
               << "      --no-plot   Do not run plot.py afterwards\n"
               << "      --resume    Checkpoint finished points in <output>.partial and skip them when restarted\n"
+              << "      --batch N   Grid points solved in lockstep per GPU, sharing their H.v launches (1..4, default 2)\n"
               << "      --reuse-shift  -f J / -f U: the chemical potential only shifts the spectrum; solve each row once\n";
 }
 
@@ -55,7 +56,7 @@ int main(int argc, char* argv[])
                                 {"type", required_argument, nullptr, 't'},       {"iterations", required_argument, nullptr, 'i'},
                                 {"epsilon", required_argument, nullptr, 'e'},    {"gpus", required_argument, nullptr, 'g'},
                                 {"lattice", required_argument, nullptr, 'l'},    {"kernel", required_argument, nullptr, 'k'},
-                                {"output", required_argument, nullptr, 'o'},     {"concurrent", required_argument, nullptr, 'c'},     {"no-plot", no_argument, nullptr, 1000},         {"reuse-shift", no_argument, nullptr, 1001},      {"resume", no_argument, nullptr, 1002},
+                                {"output", required_argument, nullptr, 'o'},     {"concurrent", required_argument, nullptr, 'c'},     {"no-plot", no_argument, nullptr, 1000},         {"reuse-shift", no_argument, nullptr, 1001},      {"resume", no_argument, nullptr, 1002},         {"batch", required_argument, nullptr, 1003},
                                 {"help", no_argument, nullptr, 'h'},             {nullptr, no_argument, nullptr, 0}};
     while (true) {
         const int o = getopt_long(argc, argv, short_opts, long_opts, nullptr);
@@ -87,6 +88,7 @@ int main(int argc, char* argv[])
             case 1000: plot = false; break;
             case 1001: opt.reuse_shift = true; break;
             case 1002: opt.resume = true; break;
+            case 1003: opt.batch = std::max(1, std::min(4, std::atoi(optarg))); break;
             case 'h':
             default: print_usage(); return 0;
         }
