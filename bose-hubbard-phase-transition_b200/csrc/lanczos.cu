@@ -311,7 +311,7 @@ __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ p
 
 __global__ void __launch_bounds__(COOP_THREADS, 2)
 k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, int passes, const double* __restrict__ w,
-            double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh)
+            double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[COOP_THREADS / 32][GT_CH];
@@ -377,6 +377,89 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
     // ---- block modified Gram-Schmidt against columns 0..i ----
     double offd = b;
     int buf = 0;
+    // Fused form (BH_COOP_FUSED=1; measured slower at m=n=12, where two blocks of 8 columns exceed L2): the update with block k (its columns re-read from L2) and the dot products with block k+1
+    // (streamed from HBM) run in the same sweep over the rows, so the two memory levels are busy together instead of in
+    // turn; same arithmetic, same order of operations per row, one grid.sync per block as before.
+    if (fused) {
+        for (int pass = 0; pass < passes; ++pass) {
+            double acc[GT_CH];
+#pragma unroll
+            for (int j = 0; j < GT_CH; ++j) acc[j] = 0.0;
+            {
+                const int nc = min(GT_CH, i + 1);
+#pragma unroll
+                for (int t = 0; t < COOP_NP; ++t) {
+                    const int64_t p = gtid + t * gsz;
+                    if (p < npair) {
+                        double2 v[GT_CH];
+#pragma unroll
+                        for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? V2[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int j = 0; j < GT_CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
+                    }
+                }
+            }
+            for (int c0 = 0; c0 <= i; c0 += GT_CH) {
+                const int nc = min(GT_CH, i + 1 - c0);
+                // finish the dot products of block c0
+#pragma unroll
+                for (int j = 0; j < GT_CH; ++j) acc[j] = bh_warp_sum(acc[j]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < GT_CH; ++j) red[wid][j] = acc[j];
+                }
+                __syncthreads();
+                double* pc = part_c + (int64_t)buf * nblk * GT_CH;
+                if (threadIdx.x < GT_CH) {
+                    double t = 0.0;
+                    for (int q = 0; q < COOP_THREADS / 32; ++q) t += red[q][threadIdx.x];
+                    pc[(int64_t)blockIdx.x * GT_CH + threadIdx.x] = t;
+                }
+                grid.sync();
+                if (wid < nc) {
+                    const double c = coop_sum_partials(pc + wid, nblk, GT_CH);
+                    if (lane == 0) cs[wid] = c;
+                } else if (wid < GT_CH && lane == 0) {
+                    cs[wid] = 0.0;
+                }
+                __syncthreads();
+                double c[GT_CH];
+#pragma unroll
+                for (int j = 0; j < GT_CH; ++j) c[j] = cs[j];
+                if (i >= c0 && i < c0 + GT_CH) alpha += cs[i - c0];                         // Lanczos.h:170
+                if (subtract && i - 1 >= c0 && i - 1 < c0 + GT_CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
+                // update with block c0, dot products with block c0 + GT_CH
+                const int c1 = c0 + GT_CH;
+                const int nc1 = (c1 <= i) ? min(GT_CH, i + 1 - c1) : 0;
+                const double2* VB = V2 + (int64_t)c0 * ld2;
+                const double2* VN = V2 + (int64_t)c1 * ld2;
+#pragma unroll
+                for (int j = 0; j < GT_CH; ++j) acc[j] = 0.0;
+#pragma unroll
+                for (int t = 0; t < COOP_NP; ++t) {
+                    const int64_t p = gtid + t * gsz;
+                    if (p < npair) {
+                        double2 v[GT_CH];
+#pragma unroll
+                        for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int j = 0; j < GT_CH; ++j) {
+                            fr[t].x = fma(-v[j].x, c[j], fr[t].x);
+                            fr[t].y = fma(-v[j].y, c[j], fr[t].y);
+                        }
+                        if (nc1 > 0) {
+#pragma unroll
+                            for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc1) ? VN[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+#pragma unroll
+                            for (int j = 0; j < GT_CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
+                        }
+                    }
+                }
+                buf ^= 1;
+                __syncthreads();  // cs / red are rewritten by the next block of columns
+            }
+        }
+    } else
     for (int pass = 0; pass < passes; ++pass) {
         for (int c0 = 0; c0 <= i; c0 += GT_CH) {
             const int nc = min(GT_CH, i + 1 - c0);
@@ -731,7 +814,8 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
                 const double* wv = ctx->d_w;
                 double* fv = ctx->d_f;
                 double th = near0;
-                void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th};
+                int fused = ctx->coop_fused;
+                void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused};
                 BH_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_coop, dim3(coop_grid), dim3(COOP_THREADS), args, 0, st));
                 BH_LAUNCHED(ctx);
                 continue;

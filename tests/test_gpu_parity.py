@@ -205,14 +205,15 @@ def test_split_matrix_free_kernel(pkg, m, n, closed, monkeypatch):
         want = chain
     cuts = sorted({1, m // 2, m - 1} | ({m // 2 - 1, m // 2 + 1} & set(range(1, m))))
     for p_cut in cuts:
-        for G in (4, 8, 16) if p_cut == m // 2 else (8,):
+        for G, UJ in ((4, 2), (8, 1), (16, 1), (2, 4)) if p_cut == m // 2 else ((4, 2),):
             monkeypatch.setenv("BH_FREE_VARIANT", "2")
             monkeypatch.setenv("BH_SPLIT_P", str(p_cut))
             monkeypatch.setenv("BH_SPLIT_G", str(G))
+            monkeypatch.setenv("BH_SPLIT_UJ", str(UJ))
             ctx = pkg.Context(0).setup(m, n, nbr)
             for k, p in enumerate(pars):
                 got = ctx.hv(*p, x, kernel=pkg.capi.HV_MATRIX_FREE, order=pkg.capi.TAG_SORTED)
                 scale = np.abs(want[k]).max()
-                assert np.abs(got - want[k]).max() <= 1e-13 * scale, (p_cut, G, np.abs(got - want[k]).max() / scale)
+                assert np.abs(got - want[k]).max() <= 1e-13 * scale, (p_cut, G, UJ, np.abs(got - want[k]).max() / scale)
                 assert np.abs(got - chain[k]).max() <= 1e-13 * scale
             ctx.close()
