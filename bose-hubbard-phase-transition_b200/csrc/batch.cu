@@ -10,6 +10,7 @@
 // doubles with one 16/32-byte access.  The per-row H.v kernel is bound by L1 tag look-ups of scattered gathers
 // (12 cache lines per warp instruction, profiles/), which the interleaving amortises over the batch.
 // Per point the arithmetic is the same sequence of operations as the single-point kernel: results are bit-identical.
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -371,7 +372,9 @@ int bh_points_lockstep(bh_ctx* ctx, int nb, const double* cJ, const double* cU, 
                        double* out3, bh_eigs_info* infos)
 {
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    const auto t_begin = std::chrono::steady_clock::now();
     BH_TRY(ensure_children(ctx, nb));
+    const auto t_children = std::chrono::steady_clock::now();
     bh_batch_hub* hub = ctx->hub;
     hub->nfib = nb;
     hub->turn = 0;
@@ -416,8 +419,11 @@ int bh_points_lockstep(bh_ctx* ctx, int nb, const double* cJ, const double* cU, 
             ctx->err = c->err;
         }
     }
-    if (getenv("BH_BATCH_VERBOSE"))
-        fprintf(stderr, "[bh] lockstep: %d points, filters applied batched %lld / single %lld (cumulative)\n", nb,
-                (long long)hub->batched_filters, (long long)hub->single_filters);
+    if (getenv("BH_BATCH_VERBOSE")) {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bh] lockstep: %d points, filters applied batched %lld / single %lld (cumulative); children %.3f s, solves %.3f s\n",
+                nb, (long long)hub->batched_filters, (long long)hub->single_filters,
+                std::chrono::duration<double>(t_children - t_begin).count(), std::chrono::duration<double>(t_end - t_children).count());
+    }
     return rc;
 }

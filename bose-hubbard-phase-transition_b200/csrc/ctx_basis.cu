@@ -492,13 +492,6 @@ int bh_ensure_staging(bh_ctx* ctx)
     if (!ctx->D) return bh_fail(ctx, BH_ERR_STATE, "no system: call bh_setup first");
     if (!ctx->d_x) BH_CUDA(ctx, cudaMalloc(&ctx->d_x, sizeof(double) * ctx->ld));
     if (!ctx->d_y) BH_CUDA(ctx, cudaMalloc(&ctx->d_y, sizeof(double) * ctx->ld));
-    const size_t need = sizeof(double) * ctx->ld * 2;
-    if (ctx->h_pinned_bytes < need) {
-        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-        ctx->h_pinned = nullptr;
-        BH_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, need));
-        ctx->h_pinned_bytes = need;
-    }
     return BH_OK;
 }
 
