@@ -71,8 +71,8 @@ __device__ __forceinline__ void load_il(const double* __restrict__ base, int idx
     }
 }
 
-template <int M, int NB, bool SRC_IL>
-__global__ void __launch_bounds__(256, (NB == 2 ? 4 : 3))
+template <int M, int NB, bool SRC_IL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_hv_chain_batch(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* __restrict__ states,
                  const double* __restrict__ dU, const __grid_constant__ BatchVecs a)
 {
@@ -149,29 +149,31 @@ k_hv_chain_batch(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* _
 
 typedef void (*batch_fn)(const BhTables*, int64_t, const uint64_t*, const double*, const BatchVecs);
 
-template <int NB, bool SRC_IL>
+template <int NB, bool SRC_IL, int MINB>
 static batch_fn batch_kernel_m(int m)
 {
     switch (m) {
-        case 6: return k_hv_chain_batch<6, NB, SRC_IL>;
-        case 7: return k_hv_chain_batch<7, NB, SRC_IL>;
-        case 8: return k_hv_chain_batch<8, NB, SRC_IL>;
-        case 9: return k_hv_chain_batch<9, NB, SRC_IL>;
-        case 10: return k_hv_chain_batch<10, NB, SRC_IL>;
-        case 11: return k_hv_chain_batch<11, NB, SRC_IL>;
-        case 12: return k_hv_chain_batch<12, NB, SRC_IL>;
-        case 13: return k_hv_chain_batch<13, NB, SRC_IL>;
-        case 14: return k_hv_chain_batch<14, NB, SRC_IL>;
-        case 15: return k_hv_chain_batch<15, NB, SRC_IL>;
-        case 16: return k_hv_chain_batch<16, NB, SRC_IL>;
+        case 6: return k_hv_chain_batch<6, NB, SRC_IL, MINB>;
+        case 7: return k_hv_chain_batch<7, NB, SRC_IL, MINB>;
+        case 8: return k_hv_chain_batch<8, NB, SRC_IL, MINB>;
+        case 9: return k_hv_chain_batch<9, NB, SRC_IL, MINB>;
+        case 10: return k_hv_chain_batch<10, NB, SRC_IL, MINB>;
+        case 11: return k_hv_chain_batch<11, NB, SRC_IL, MINB>;
+        case 12: return k_hv_chain_batch<12, NB, SRC_IL, MINB>;
+        case 13: return k_hv_chain_batch<13, NB, SRC_IL, MINB>;
+        case 14: return k_hv_chain_batch<14, NB, SRC_IL, MINB>;
+        case 15: return k_hv_chain_batch<15, NB, SRC_IL, MINB>;
+        case 16: return k_hv_chain_batch<16, NB, SRC_IL, MINB>;
     }
     return nullptr;
 }
 
 static batch_fn batch_kernel(int m, int nb, bool src_il)
 {
-    if (nb == 2) return src_il ? batch_kernel_m<2, true>(m) : batch_kernel_m<2, false>(m);
-    if (nb == 4) return src_il ? batch_kernel_m<4, true>(m) : batch_kernel_m<4, false>(m);
+    static const int minb4 = getenv("BH_BATCH4_MINB") ? atoi(getenv("BH_BATCH4_MINB")) : 3;
+    if (nb == 2) return src_il ? batch_kernel_m<2, true, 4>(m) : batch_kernel_m<2, false, 4>(m);
+    if (nb == 4 && minb4 == 4) return src_il ? batch_kernel_m<4, true, 4>(m) : batch_kernel_m<4, false, 4>(m);
+    if (nb == 4) return src_il ? batch_kernel_m<4, true, 3>(m) : batch_kernel_m<4, false, 3>(m);
     return nullptr;
 }
 

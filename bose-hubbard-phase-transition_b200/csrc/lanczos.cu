@@ -309,13 +309,14 @@ __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ p
     return bh_warp_sum(t);
 }
 
+template <int CH>
 __global__ void __launch_bounds__(COOP_THREADS, 2)
 k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, int passes, const double* __restrict__ w,
             double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double red[COOP_THREADS / 32][GT_CH];
-    __shared__ double cs[GT_CH];
+    __shared__ double red[COOP_THREADS / 32][CH];
+    __shared__ double cs[CH];
     __shared__ double sh_val;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nblk = gridDim.x;
@@ -323,7 +324,7 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
     const int64_t gsz = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double* part_a = part;                         // [nblk]
     double* part_n = part + nblk;                  // [nblk]
-    double* part_c = part + 2 * (int64_t)nblk;     // [2][nblk][GT_CH]
+    double* part_c = part + 2 * (int64_t)nblk;     // [2][nblk][CH]
     const double2* w2 = reinterpret_cast<const double2*>(w);
     const double2* vi2 = reinterpret_cast<const double2*>(V + (int64_t)i * ld);
     const double2* vp2 = reinterpret_cast<const double2*>(V + (int64_t)(i > 0 ? i - 1 : 0) * ld);
@@ -382,76 +383,76 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
     // turn; same arithmetic, same order of operations per row, one grid.sync per block as before.
     if (fused) {
         for (int pass = 0; pass < passes; ++pass) {
-            double acc[GT_CH];
+            double acc[CH];
 #pragma unroll
-            for (int j = 0; j < GT_CH; ++j) acc[j] = 0.0;
+            for (int j = 0; j < CH; ++j) acc[j] = 0.0;
             {
-                const int nc = min(GT_CH, i + 1);
+                const int nc = min(CH, i + 1);
 #pragma unroll
                 for (int t = 0; t < COOP_NP; ++t) {
                     const int64_t p = gtid + t * gsz;
                     if (p < npair) {
-                        double2 v[GT_CH];
+                        double2 v[CH];
 #pragma unroll
-                        for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? V2[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+                        for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? V2[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
-                        for (int j = 0; j < GT_CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
+                        for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
                     }
                 }
             }
-            for (int c0 = 0; c0 <= i; c0 += GT_CH) {
-                const int nc = min(GT_CH, i + 1 - c0);
+            for (int c0 = 0; c0 <= i; c0 += CH) {
+                const int nc = min(CH, i + 1 - c0);
                 // finish the dot products of block c0
 #pragma unroll
-                for (int j = 0; j < GT_CH; ++j) acc[j] = bh_warp_sum(acc[j]);
+                for (int j = 0; j < CH; ++j) acc[j] = bh_warp_sum(acc[j]);
                 if (lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < GT_CH; ++j) red[wid][j] = acc[j];
+                    for (int j = 0; j < CH; ++j) red[wid][j] = acc[j];
                 }
                 __syncthreads();
-                double* pc = part_c + (int64_t)buf * nblk * GT_CH;
-                if (threadIdx.x < GT_CH) {
+                double* pc = part_c + (int64_t)buf * nblk * CH;
+                if (threadIdx.x < CH) {
                     double t = 0.0;
                     for (int q = 0; q < COOP_THREADS / 32; ++q) t += red[q][threadIdx.x];
-                    pc[(int64_t)blockIdx.x * GT_CH + threadIdx.x] = t;
+                    pc[(int64_t)blockIdx.x * CH + threadIdx.x] = t;
                 }
                 grid.sync();
                 if (wid < nc) {
-                    const double c = coop_sum_partials(pc + wid, nblk, GT_CH);
+                    const double c = coop_sum_partials(pc + wid, nblk, CH);
                     if (lane == 0) cs[wid] = c;
-                } else if (wid < GT_CH && lane == 0) {
+                } else if (wid < CH && lane == 0) {
                     cs[wid] = 0.0;
                 }
                 __syncthreads();
-                double c[GT_CH];
+                double c[CH];
 #pragma unroll
-                for (int j = 0; j < GT_CH; ++j) c[j] = cs[j];
-                if (i >= c0 && i < c0 + GT_CH) alpha += cs[i - c0];                         // Lanczos.h:170
-                if (subtract && i - 1 >= c0 && i - 1 < c0 + GT_CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
-                // update with block c0, dot products with block c0 + GT_CH
-                const int c1 = c0 + GT_CH;
-                const int nc1 = (c1 <= i) ? min(GT_CH, i + 1 - c1) : 0;
+                for (int j = 0; j < CH; ++j) c[j] = cs[j];
+                if (i >= c0 && i < c0 + CH) alpha += cs[i - c0];                         // Lanczos.h:170
+                if (subtract && i - 1 >= c0 && i - 1 < c0 + CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
+                // update with block c0, dot products with block c0 + CH
+                const int c1 = c0 + CH;
+                const int nc1 = (c1 <= i) ? min(CH, i + 1 - c1) : 0;
                 const double2* VB = V2 + (int64_t)c0 * ld2;
                 const double2* VN = V2 + (int64_t)c1 * ld2;
 #pragma unroll
-                for (int j = 0; j < GT_CH; ++j) acc[j] = 0.0;
+                for (int j = 0; j < CH; ++j) acc[j] = 0.0;
 #pragma unroll
                 for (int t = 0; t < COOP_NP; ++t) {
                     const int64_t p = gtid + t * gsz;
                     if (p < npair) {
-                        double2 v[GT_CH];
+                        double2 v[CH];
 #pragma unroll
-                        for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+                        for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
-                        for (int j = 0; j < GT_CH; ++j) {
+                        for (int j = 0; j < CH; ++j) {
                             fr[t].x = fma(-v[j].x, c[j], fr[t].x);
                             fr[t].y = fma(-v[j].y, c[j], fr[t].y);
                         }
                         if (nc1 > 0) {
 #pragma unroll
-                            for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc1) ? VN[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+                            for (int j = 0; j < CH; ++j) v[j] = (j < nc1) ? VN[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
-                            for (int j = 0; j < GT_CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
+                            for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
                         }
                     }
                 }
@@ -461,58 +462,58 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
         }
     } else
     for (int pass = 0; pass < passes; ++pass) {
-        for (int c0 = 0; c0 <= i; c0 += GT_CH) {
-            const int nc = min(GT_CH, i + 1 - c0);
+        for (int c0 = 0; c0 <= i; c0 += CH) {
+            const int nc = min(CH, i + 1 - c0);
             const double2* VB = V2 + (int64_t)c0 * ld2;
-            double acc[GT_CH];
+            double acc[CH];
 #pragma unroll
-            for (int j = 0; j < GT_CH; ++j) acc[j] = 0.0;
+            for (int j = 0; j < CH; ++j) acc[j] = 0.0;
 #pragma unroll
             for (int t = 0; t < COOP_NP; ++t) {
                 const int64_t p = gtid + t * gsz;
                 if (p < npair) {
-                    double2 v[GT_CH];
+                    double2 v[CH];
 #pragma unroll
-                    for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+                    for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
-                    for (int j = 0; j < GT_CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
+                    for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
                 }
             }
 #pragma unroll
-            for (int j = 0; j < GT_CH; ++j) acc[j] = bh_warp_sum(acc[j]);
+            for (int j = 0; j < CH; ++j) acc[j] = bh_warp_sum(acc[j]);
             if (lane == 0) {
 #pragma unroll
-                for (int j = 0; j < GT_CH; ++j) red[wid][j] = acc[j];
+                for (int j = 0; j < CH; ++j) red[wid][j] = acc[j];
             }
             __syncthreads();
-            double* pc = part_c + (int64_t)buf * nblk * GT_CH;
-            if (threadIdx.x < GT_CH) {
+            double* pc = part_c + (int64_t)buf * nblk * CH;
+            if (threadIdx.x < CH) {
                 double t = 0.0;
                 for (int q = 0; q < COOP_THREADS / 32; ++q) t += red[q][threadIdx.x];
-                pc[(int64_t)blockIdx.x * GT_CH + threadIdx.x] = t;
+                pc[(int64_t)blockIdx.x * CH + threadIdx.x] = t;
             }
             grid.sync();
             if (wid < nc) {
-                const double c = coop_sum_partials(pc + wid, nblk, GT_CH);
+                const double c = coop_sum_partials(pc + wid, nblk, CH);
                 if (lane == 0) cs[wid] = c;
-            } else if (wid < GT_CH && lane == 0) {
+            } else if (wid < CH && lane == 0) {
                 cs[wid] = 0.0;
             }
             __syncthreads();
-            double c[GT_CH];
+            double c[CH];
 #pragma unroll
-            for (int j = 0; j < GT_CH; ++j) c[j] = cs[j];
-            if (i >= c0 && i < c0 + GT_CH) alpha += cs[i - c0];                         // Lanczos.h:170
-            if (subtract && i - 1 >= c0 && i - 1 < c0 + GT_CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
+            for (int j = 0; j < CH; ++j) c[j] = cs[j];
+            if (i >= c0 && i < c0 + CH) alpha += cs[i - c0];                         // Lanczos.h:170
+            if (subtract && i - 1 >= c0 && i - 1 < c0 + CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
 #pragma unroll
             for (int t = 0; t < COOP_NP; ++t) {
                 const int64_t p = gtid + t * gsz;
                 if (p < npair) {
-                    double2 v[GT_CH];
+                    double2 v[CH];
 #pragma unroll
-                    for (int j = 0; j < GT_CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+                    for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
-                    for (int j = 0; j < GT_CH; ++j) {
+                    for (int j = 0; j < CH; ++j) {
                         fr[t].x = fma(-v[j].x, c[j], fr[t].x);
                         fr[t].y = fma(-v[j].y, c[j], fr[t].y);
                     }
@@ -766,7 +767,10 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
     int coop_grid = 0;
     if (ctx->coop && !dist) {
         int bps = 0;
-        BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop, COOP_THREADS, 0));
+        if (ctx->coop_ch == 4)
+            BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<4>, COOP_THREADS, 0));
+        else
+            BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH>, COOP_THREADS, 0));
         bps = std::min(bps, 2);
         const int64_t npair = (D + 1) / 2;
         if (bps >= 1 && npair <= (int64_t)ctx->sm_count * bps * COOP_THREADS * COOP_NP) {
@@ -816,7 +820,8 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
                 double th = near0;
                 int fused = ctx->coop_fused;
                 void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused};
-                BH_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_step_coop, dim3(coop_grid), dim3(COOP_THREADS), args, 0, st));
+                BH_CUDA(ctx, cudaLaunchCooperativeKernel(ctx->coop_ch == 4 ? (void*)k_step_coop<4> : (void*)k_step_coop<GT_CH>, dim3(coop_grid),
+                                                     dim3(COOP_THREADS), args, 0, st));
                 BH_LAUNCHED(ctx);
                 continue;
             }
