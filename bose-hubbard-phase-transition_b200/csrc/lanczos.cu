@@ -673,6 +673,64 @@ k_compress_tiled(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, 
     }
 }
 
+// K6, wider register tile: a thread owns 4 rows x 8 columns (32 accumulators), a CTA 256 rows x 32 columns per sweep.
+// Per j the warp reads 8 shared-memory wavefronts of V (4 consecutive doubles per lane) and 2 broadcast wavefronts of Y for
+// 1024 FMAs (16 issue cycles of the FP64 pipe): bound by the FP64 rate instead of by shared memory like the 4 x 4 tile.
+#define CT8_ROWS 256
+__global__ void __launch_bounds__(256, 2)
+k_compress_tiled8(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, const double* __restrict__ Y)
+{
+    extern __shared__ __align__(16) double sm3[];
+    double* vt = sm3;                            // [ncv][CT8_ROWS]
+    double* yc = sm3 + (size_t)ncv * CT8_ROWS;   // [ncv][CT_COLS]
+    const int64_t r0 = (int64_t)blockIdx.x * CT8_ROWS;
+    const int rg = threadIdx.x & 63, cgp = threadIdx.x >> 6;  // 64 row groups (4 rows) x 4 column groups (8 columns)
+    for (int idx = threadIdx.x; idx < ncv * CT8_ROWS; idx += blockDim.x) {
+        const int j = idx / CT8_ROWS, r = idx % CT8_ROWS;
+        vt[idx] = (r0 + r < D) ? V[(int64_t)j * ld + r0 + r] : 0.0;
+    }
+    for (int c0 = 0; c0 < k; c0 += CT_COLS) {
+        const int nck = min(CT_COLS, k - c0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < ncv * CT_COLS; idx += blockDim.x) {
+            const int j = idx / CT_COLS, c = idx % CT_COLS;
+            yc[idx] = (c < nck) ? Y[(size_t)(c0 + c) * ncv + j] : 0.0;
+        }
+        __syncthreads();
+        double acc[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+        for (int j = 0; j < ncv; ++j) {
+            const double2 a01 = *reinterpret_cast<const double2*>(vt + j * CT8_ROWS + rg * 4);
+            const double2 a23 = *reinterpret_cast<const double2*>(vt + j * CT8_ROWS + rg * 4 + 2);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+            double b[8];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const double2 t = *reinterpret_cast<const double2*>(yc + j * CT_COLS + cgp * 8 + 2 * h);
+                b[2 * h] = t.x;
+                b[2 * h + 1] = t.y;
+            }
+#pragma unroll
+            for (int ra = 0; ra < 4; ++ra)
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb) acc[ra][cb] = fma(a[ra], b[cb], acc[ra][cb]);
+        }
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) {
+            const int c = cgp * 8 + cb;
+            if (c < nck) {
+                double* dst = V + (int64_t)(c0 + c) * ld + r0 + rg * 4;
+#pragma unroll
+                for (int ra = 0; ra < 4; ++ra)
+                    if (r0 + rg * 4 + ra < D) dst[ra] = acc[ra][cb];
+            }
+        }
+    }
+}
+
 int bh_ensure_workspace(bh_ctx* ctx, int ncv)
 {
     if (!ctx->D) return bh_fail(ctx, BH_ERR_STATE, "no system: call bh_setup first");
@@ -755,6 +813,9 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
     const size_t tiled_smem = sizeof(double) * (size_t)ncv * (CT_ROWS + CT_COLS);
     const bool tiled = tiled_smem <= 200 * 1024 && ctx->compress_tiled;
     if (tiled) BH_CUDA(ctx, cudaFuncSetAttribute(k_compress_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
+    const size_t tiled8_smem = sizeof(double) * (size_t)ncv * (CT8_ROWS + CT_COLS);
+    const bool tiled8 = tiled && ctx->compress_tiled >= 2 && tiled8_smem <= 110 * 1024;
+    if (tiled8) BH_CUDA(ctx, cudaFuncSetAttribute(k_compress_tiled8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled8_smem));
     const size_t compress_smem = sizeof(double) * ((size_t)ncv * CRsel + (size_t)CK * ncv);
     if (compress_smem > 48 * 1024) {
         if (CRsel == 64)
@@ -910,7 +971,9 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
         if (knew > ncv - 1) knew = ncv - 1;
         // K6: V[:, 0..knew) <- V Y[:, 0..knew)
         BH_H2D(ctx, ctx->d_small, Y.data(), sizeof(double) * (size_t)ncv * knew);
-        if (tiled)
+        if (tiled8)
+            k_compress_tiled8<<<nblocks(D, CT8_ROWS), 256, tiled8_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
+        else if (tiled)
             k_compress_tiled<<<nblocks(D, CT_ROWS), 256, tiled_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
         else if (CRsel == 64)
             k_compress<64><<<nblocks(D, 64), 256, compress_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
