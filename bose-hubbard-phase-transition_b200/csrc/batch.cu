@@ -364,6 +364,9 @@ static int ensure_children(bh_ctx* ctx, int nb)
         c->spdm_scratch_bytes = 0;
         c->ws_ncv = 0;
         for (int q = 0; q < 3; ++q) c->d_cheb[q] = nullptr;
+        c->d_hv_block = nullptr;
+        c->hv_block_cols = 0;
+        c->d_gram_part = nullptr;
         ctx->children.push_back(c);
     }
     return BH_OK;

@@ -115,6 +115,10 @@ struct bh_ctx {
     double cheb_margin = 0.05;  // cut >= theta_{nev-1} + margin * (theta_{nev-1} - theta_0)   (env BH_CHEB_MARGIN)
     double cheb_frac = 0.08;    // cut >= theta_0 + frac * (hi - theta_0)                       (env BH_CHEB_FRAC)
     double* d_cheb[3] = {nullptr, nullptr, nullptr};
+    int rr_gram = 1;                 // Rayleigh-Ritz of H: W = H V, then one Gram pass V^T W (env BH_RR_GRAM; 0 = ncv transposed products)
+    double* d_hv_block = nullptr;    // W, hv_block_cols columns of ld doubles (lazy)
+    int hv_block_cols = 0;
+    double* d_gram_part = nullptr;   // per-CTA partial Gram matrices
     int compress_tiled = 2;  // restart GEMM (env BH_COMPRESS_TILED): 0 shared-memory rows, 1 4x4 register tiles, 2 4x8 register tiles
     int coop_ch = 8;       // basis columns per block of the cooperative step's block Gram-Schmidt (env BH_COOP_CH: 4 or 8)
     int coop_fused = 0;    // cooperative step: update with block k fused with the dot products of block k+1 (env BH_COOP_FUSED)

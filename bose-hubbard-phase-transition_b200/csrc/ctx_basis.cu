@@ -70,6 +70,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     if (const char* v = getenv("BH_SELL_SIGMA")) ctx->sell_sigma = std::min(1024, std::max(32, atoi(v) / 32 * 32));
     if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
     if (const char* v = getenv("BH_COOP_FUSED")) ctx->coop_fused = atoi(v);
+    if (const char* v = getenv("BH_RR_GRAM")) ctx->rr_gram = atoi(v);
     if (const char* v = getenv("BH_COOP_CH")) ctx->coop_ch = (atoi(v) == 4) ? 4 : 8;
     if (const char* v = getenv("BH_COMPRESS_TILED")) ctx->compress_tiled = atoi(v);
     if (const char* v = getenv("BH_CHEB_DEGREE")) ctx->cheb_degree = std::max(1, atoi(v));
@@ -97,6 +98,9 @@ void bh_release_workspace(bh_ctx* ctx)
     free_dev(ctx->d_counter); ctx->d_counter = nullptr;
     free_dev(ctx->d_small); ctx->d_small = nullptr;
     for (int q = 0; q < 3; ++q) { free_dev(ctx->d_cheb[q]); ctx->d_cheb[q] = nullptr; }
+    free_dev(ctx->d_hv_block); ctx->d_hv_block = nullptr;
+    ctx->hv_block_cols = 0;
+    free_dev(ctx->d_gram_part); ctx->d_gram_part = nullptr;
     free_dev(ctx->d_spdm_scratch); ctx->d_spdm_scratch = nullptr;
     ctx->spdm_scratch_bytes = 0;
     free_dev(ctx->d_x); ctx->d_x = nullptr;

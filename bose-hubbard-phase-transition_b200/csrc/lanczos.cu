@@ -731,6 +731,73 @@ k_compress_tiled8(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Gram product M = V^T W (ncv x ncv, ncv <= GRAM_N) for the Rayleigh-Ritz step of the accelerated solver: one pass
+// over V and W instead of ncv transposed products that each re-read V.  A CTA stages GRAM_R rows of both matrices
+// in shared memory ([row][column], padded), every thread keeps a 3 x 3 tile of M in registers across all its row
+// tiles; per-CTA partials are combined in a fixed order by k_gram_reduce (deterministic).
+// ---------------------------------------------------------------------------------------------------------
+#define GRAM_N 48
+#define GRAM_R 32
+#define GRAM_LD 49
+__global__ void __launch_bounds__(256, 2)
+k_gram(int64_t D, int64_t ld, const double* __restrict__ V, const double* __restrict__ W, int ncv, double* __restrict__ part)
+{
+    __shared__ double vt[GRAM_R * GRAM_LD];
+    __shared__ double wt[GRAM_R * GRAM_LD];
+    const int ta = threadIdx.x >> 4, tb = threadIdx.x & 15;  // tile (3 ta .. 3 ta + 2) x (3 tb .. 3 tb + 2)
+    double acc[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) acc[a][b] = 0.0;
+    for (int idx = threadIdx.x; idx < GRAM_R * GRAM_LD; idx += blockDim.x) {
+        vt[idx] = 0.0;
+        wt[idx] = 0.0;
+    }
+    const int64_t ntiles = (D + GRAM_R - 1) / GRAM_R;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * GRAM_R;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < ncv * GRAM_R; idx += blockDim.x) {
+            const int j = idx / GRAM_R, r = idx % GRAM_R;
+            const bool in = r0 + r < D;
+            vt[r * GRAM_LD + j] = in ? V[(int64_t)j * ld + r0 + r] : 0.0;
+            wt[r * GRAM_LD + j] = in ? W[(int64_t)j * ld + r0 + r] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < GRAM_R; ++r) {
+            double a[3], b[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                a[q] = vt[r * GRAM_LD + 3 * ta + q];
+                b[q] = wt[r * GRAM_LD + 3 * tb + q];
+            }
+#pragma unroll
+            for (int x = 0; x < 3; ++x)
+#pragma unroll
+                for (int y = 0; y < 3; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+        }
+    }
+    double* dst = part + (size_t)blockIdx.x * GRAM_N * GRAM_N;
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int y = 0; y < 3; ++y) dst[(3 * ta + x) * GRAM_N + 3 * tb + y] = acc[x][y];
+}
+
+// M[a + b * ncv] = sum over CTAs of part[cta][a][b], fixed order
+__global__ void k_gram_reduce(int nparts, const double* __restrict__ part, int ncv, double* __restrict__ M)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncv * ncv) return;
+    const int a = idx % ncv, b = idx / ncv;
+    double t = 0.0;
+    for (int p = 0; p < nparts; ++p) t += part[(size_t)p * GRAM_N * GRAM_N + a * GRAM_N + b];
+    M[a + (size_t)b * ncv] = t;
+}
+
 int bh_ensure_workspace(bh_ctx* ctx, int ncv)
 {
     if (!ctx->D) return bh_fail(ctx, BH_ERR_STATE, "no system: call bh_setup first");
@@ -1118,7 +1185,23 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
         const int64_t n = ctx->nloc, ld = ctx->ld;
         const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(n, VEC_THREADS), (int64_t)ctx->sm_count * 4));
         const bool dist = ctx->partitioned && ctx->world > 1;
-        for (int col = 0; col < ncv; ++col) {
+        const bool gram = !dist && ncv <= GRAM_N && ctx->rr_gram;
+        if (gram) {
+            // W = H V column by column, then M = V^T W in one pass over both (k_gram)
+            const int nparts = ctx->sm_count * 2;
+            if (ctx->hv_block_cols < ncv) {
+                if (ctx->d_hv_block) cudaFree(ctx->d_hv_block);
+                ctx->d_hv_block = nullptr;
+                BH_CUDA(ctx, cudaMalloc(&ctx->d_hv_block, sizeof(double) * (size_t)ld * ncv));
+                ctx->hv_block_cols = ncv;
+            }
+            if (!ctx->d_gram_part) BH_CUDA(ctx, cudaMalloc(&ctx->d_gram_part, sizeof(double) * (size_t)nparts * GRAM_N * GRAM_N));
+            for (int col = 0; col < ncv; ++col) BH_TRY(plain(ctx->d_V + (int64_t)col * ld, ctx->d_hv_block + (int64_t)col * ld));
+            k_gram<<<nparts, 256, 0, ctx->stream>>>(n, ld, ctx->d_V, ctx->d_hv_block, ncv, ctx->d_gram_part);
+            k_gram_reduce<<<(ncv * ncv + 255) / 256, 256, 0, ctx->stream>>>(nparts, ctx->d_gram_part, ncv, ctx->d_small);
+            ctx->launches += 2;
+        }
+        for (int col = 0; col < ncv && !gram; ++col) {
             BH_TRY(plain(ctx->d_V + (int64_t)col * ld, ctx->d_w));
             k_gemv_t<true><<<G, VEC_THREADS, 0, ctx->stream>>>(n, ld, ctx->d_V, 0, ncv, ctx->d_w, ctx->d_scal, 0, 0, ctx->d_part,
                                                               ctx->d_counter, 1);
