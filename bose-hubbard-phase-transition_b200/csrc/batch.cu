@@ -59,6 +59,24 @@ struct BatchVecs {
     double s1[BH_MAX_BATCH], s2[BH_MAX_BATCH], s3[BH_MAX_BATCH];
 };
 
+// four interleaved doubles with ONE 256-bit access (sm_100: LDG.E.256 / STG.E.256): one L1 tag look-up per lane and hop
+__device__ __forceinline__ void load_il(const double* __restrict__ base, int idx, double (&v)[4])
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                 : "l"(base + (size_t)idx * 4));
+}
+
+__device__ __forceinline__ void store_il(double* base, size_t row, const double (&v)[4])
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(base + row * 4), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+__device__ __forceinline__ void store_il(double* base, size_t row, const double (&v)[2])
+{
+    *reinterpret_cast<double2*>(base + row * 2) = make_double2(v[0], v[1]);
+}
+
 template <int NB>
 __device__ __forceinline__ void load_il(const double* __restrict__ base, int idx, double (&v)[NB])
 {
@@ -92,7 +110,7 @@ k_hv_chain_batch(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* _
             for (int b = 0; b < NB; ++b) v[b] = 0.0;
             if (cond) {
                 if (SRC_IL) {
-                    load_il<NB>(a.xi, idx, v);
+                    load_il(a.xi, idx, v);
                 } else {
 #pragma unroll
                     for (int b = 0; b < NB; ++b) v[b] = __ldg(a.xs[b] + idx);
@@ -119,14 +137,14 @@ k_hv_chain_batch(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* _
         }
         double xv[NB], zv[NB], out[NB];
         if (SRC_IL) {
-            load_il<NB>(a.xi, kk, xv);
+            load_il(a.xi, kk, xv);
         } else {
 #pragma unroll
             for (int b = 0; b < NB; ++b) xv[b] = a.xs[b][l];
         }
         const double du = dU[l];
         const bool zil = a.zi != nullptr, zsep = a.zs[0] != nullptr;
-        if (zil) load_il<NB>(a.zi, kk, zv);
+        if (zil) load_il(a.zi, kk, zv);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const double diag = __dadd_rn(__dmul_rn(du, a.cU[b]), a.shift[b]);
@@ -137,9 +155,7 @@ k_hv_chain_batch(const BhTables* __restrict__ gtab, int64_t D, const uint64_t* _
             out[b] = o;
         }
         if (a.yi) {
-            double2* p = reinterpret_cast<double2*>(a.yi + (size_t)l * NB);
-#pragma unroll
-            for (int h = 0; h < NB / 2; ++h) p[h] = make_double2(out[2 * h], out[2 * h + 1]);
+            store_il(a.yi, (size_t)l, out);
         } else {
 #pragma unroll
             for (int b = 0; b < NB; ++b) a.ys[b][l] = out[b];
@@ -372,9 +388,10 @@ static int ensure_children(bh_ctx* ctx, int nb)
     return BH_OK;
 }
 
-// nb (2..4) grid points in lockstep; results as bh_point.
-int bh_points_lockstep(bh_ctx* ctx, int nb, const double* cJ, const double* cU, const double* cmu, int nb_eigen, int kernel,
-                       double* out3, bh_eigs_info* infos)
+// npoints grid points on nb (2..4) lockstep solves; a solve that finishes its point takes the next one from the list, so
+// the batch stays full until the list runs out.  Results as bh_point, point by point.
+int bh_points_lockstep(bh_ctx* ctx, int nb, int64_t npoints, const double* cJ, const double* cU, const double* cmu, int nb_eigen,
+                       int kernel, double* out3, bh_eigs_info* infos)
 {
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     const auto t_begin = std::chrono::steady_clock::now();
@@ -385,23 +402,32 @@ int bh_points_lockstep(bh_ctx* ctx, int nb, const double* cJ, const double* cU, 
     hub->turn = 0;
     for (int j = 0; j < BH_MAX_BATCH; ++j) hub->done[j] = hub->parked[j] = false;
     int rcs[BH_MAX_BATCH] = {BH_OK, BH_OK, BH_OK, BH_OK};
+    int64_t next_point = 0;  // guarded by the baton (only the running fiber touches it)
+    bool stop = false;
     std::vector<std::thread> threads;
     for (int i = 0; i < nb; ++i) {
         bh_ctx* c = ctx->children[i];
         c->stream = ctx->stream;
         c->cheb_degree = ctx->cheb_degree;
-        threads.emplace_back([=, &rcs] {
+        threads.emplace_back([=, &rcs, &next_point, &stop] {
             {
                 std::unique_lock<std::mutex> lk(hub->mu);
                 hub->cv.wait(lk, [&] { return hub->turn == i; });
             }
-            int rc;
-            try {
-                rc = bh_point(c, cJ[i], cU[i], cmu[i], nb_eigen, kernel, out3 + 3 * i, nullptr, nullptr, infos ? infos + i : nullptr);
-            } catch (...) {
-                rc = bh_fail(c, BH_ERR_STATE, "exception inside a lockstep solve");
+            for (;;) {
+                if (stop || next_point >= npoints) break;
+                const int64_t p = next_point++;
+                int rc;
+                try {
+                    rc = bh_point(c, cJ[p], cU[p], cmu[p], nb_eigen, kernel, out3 + 3 * p, nullptr, nullptr, infos ? infos + p : nullptr);
+                } catch (...) {
+                    rc = bh_fail(c, BH_ERR_STATE, "exception inside a lockstep solve");
+                }
+                if (rc != BH_OK) {
+                    rcs[i] = rc;
+                    stop = true;
+                }
             }
-            rcs[i] = rc;
             // leave: pass the baton; if every remaining live solve is parked, launch their filters first
             std::unique_lock<std::mutex> lk(hub->mu);
             hub->done[i] = true;
@@ -426,8 +452,8 @@ int bh_points_lockstep(bh_ctx* ctx, int nb, const double* cJ, const double* cU, 
     }
     if (getenv("BH_BATCH_VERBOSE")) {
         const auto t_end = std::chrono::steady_clock::now();
-        fprintf(stderr, "[bh] lockstep: %d points, filters applied batched %lld / single %lld (cumulative); children %.3f s, solves %.3f s\n",
-                nb, (long long)hub->batched_filters, (long long)hub->single_filters,
+        fprintf(stderr, "[bh] lockstep: %lld points, filters applied batched %lld / single %lld (cumulative); children %.3f s, solves %.3f s\n",
+                (long long)npoints, (long long)hub->batched_filters, (long long)hub->single_filters,
                 std::chrono::duration<double>(t_children - t_begin).count(), std::chrono::duration<double>(t_end - t_children).count());
     }
     return rc;

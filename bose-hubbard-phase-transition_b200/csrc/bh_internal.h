@@ -173,8 +173,8 @@ int bh_release_system(bh_ctx* ctx);
 void bh_release_workspace(bh_ctx* ctx);  // Krylov workspace, staging, scratch (everything a lockstep child owns)
 // lockstep batching (batch.cu)
 bool bh_batch_supported(const bh_ctx* ctx, int kernel);
-int bh_points_lockstep(bh_ctx* ctx, int nb, const double* cJ, const double* cU, const double* cmu, int nb_eigen, int kernel,
-                       double* out3, bh_eigs_info* infos);
+int bh_points_lockstep(bh_ctx* ctx, int nb, int64_t npoints, const double* cJ, const double* cU, const double* cmu, int nb_eigen,
+                       int kernel, double* out3, bh_eigs_info* infos);
 int bh_batch_filter(bh_ctx* child, const double* x, double* y, double c, double e, double cJ, double cU, double cmu, int d,
                     bool* handled);
 void bh_batch_release(bh_ctx* ctx);

@@ -214,15 +214,10 @@ extern "C" int bh_points(bh_ctx* ctx, const double* cJ, const double* cU, const 
                          int kernel, double* out3, bh_eigs_info* infos)
 {
     if (!ctx || !cJ || !cU || !cmu || !out3 || npoints < 0) return bh_fail(ctx, BH_ERR_ARG, "bh_points: bad argument");
-    // lockstep batching (batch.cu): groups of ctx->batch points share their H.v launches; same results point by point
-    const bool lockstep = ctx->batch >= 2 && ctx->D && nb_eigen >= 3 && bh_batch_supported(ctx, kernel);
-    for (int64_t p = 0; p < npoints;) {
-        const int nb = lockstep ? (int)std::min<int64_t>(ctx->batch, npoints - p) : 1;
-        if (nb >= 2)
-            BH_TRY(bh_points_lockstep(ctx, nb, cJ + p, cU + p, cmu + p, nb_eigen, kernel, out3 + 3 * p, infos ? infos + p : nullptr));
-        else
-            BH_TRY(bh_point(ctx, cJ[p], cU[p], cmu[p], nb_eigen, kernel, out3 + 3 * p, nullptr, nullptr, infos ? infos + p : nullptr));
-        p += nb;
-    }
+    // lockstep batching (batch.cu): ctx->batch solves run together and share their H.v launches; same results point by point
+    if (ctx->batch >= 2 && npoints >= 2 && ctx->D && nb_eigen >= 3 && bh_batch_supported(ctx, kernel))
+        return bh_points_lockstep(ctx, (int)std::min<int64_t>(ctx->batch, npoints), npoints, cJ, cU, cmu, nb_eigen, kernel, out3, infos);
+    for (int64_t p = 0; p < npoints; ++p)
+        BH_TRY(bh_point(ctx, cJ[p], cU[p], cmu[p], nb_eigen, kernel, out3 + 3 * p, nullptr, nullptr, infos ? infos + p : nullptr));
     return BH_OK;
 }

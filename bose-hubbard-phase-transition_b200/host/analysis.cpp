@@ -128,10 +128,12 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
             try {
                 const int B = std::max(1, std::min(4, opt.batch));
                 for (;;) {
-                    // up to B tasks per call: bh_points solves them in lockstep (shared H.v launches, same results)
-                    int ts[4], nt = 0;
-                    double cJ[4], cU[4], cmu[4], p1s[4], out3[12];
-                    while (nt < B) {
+                    // a chunk of tasks per call: bh_points keeps B solves in lockstep (shared H.v launches, same results) and
+                    // refills a finished solve from the chunk
+                    const int chunk = B > 1 ? std::min(16, 4 * B) : 1;
+                    int ts[16], nt = 0;
+                    double cJ[16], cU[16], cmu[16], p1s[16], out3[48];
+                    while (nt < chunk) {
                         const int t = next.fetch_add(1);
                         if (t >= ntasks) break;
                         const int i = shift_rows ? t : t / g.num2, j = shift_rows ? 0 : t % g.num2;

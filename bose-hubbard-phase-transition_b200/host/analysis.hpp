@@ -14,7 +14,7 @@ struct ExactOptions {
     bool reuse_shift = false;      // -f J / -f U: the second parameter only shifts the spectrum; solve each row once
     int contexts_per_gpu = 1;      // concurrent grid points per GPU (each on its own context)
     int kernel = 0;                // BH_HV_STORED (0) or BH_HV_MATRIX_FREE (1)
-    int batch = 2;                 // grid points solved in lockstep per context (bh_ctx_set_batch; effective for chains + matrix-free)
+    int batch = 4;                 // grid points solved in lockstep per context (bh_ctx_set_batch; effective for chains + matrix-free)
     int lx = 0, ly = 0, lz = 0;    // lx*ly*lz == m selects a periodic box; all zero = closed chain (reference)
     bool closed = true;
     std::string output = "phase.txt";

@@ -36,7 +36,7 @@ static void print_usage()
               << "  -c, --concurrent Grid points solved concurrently per GPU (default 1)\n"
               << "      --no-plot   Do not run plot.py afterwards\n"
               << "      --resume    Checkpoint finished points in <output>.partial and skip them when restarted\n"
-              << "      --batch N   Grid points solved in lockstep per GPU, sharing their H.v launches (1..4, default 2)\n"
+              << "      --batch N   Grid points solved in lockstep per GPU, sharing their H.v launches (1..4, default 4)\n"
               << "      --reuse-shift  -f J / -f U: the chemical potential only shifts the spectrum; solve each row once\n";
 }
 
