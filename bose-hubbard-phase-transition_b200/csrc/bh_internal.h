@@ -121,7 +121,10 @@ struct bh_ctx {
     double* d_gram_part = nullptr;   // per-CTA partial Gram matrices
     int compress_tiled = 2;  // restart GEMM (env BH_COMPRESS_TILED): 0 shared-memory rows, 1 4x4 register tiles, 2 4x8 register tiles
     int coop_ch = 8;       // basis columns per block of the cooperative step's block Gram-Schmidt (env BH_COOP_CH: 4 or 8)
-    int coop_fused = 0;    // cooperative step: update with block k fused with the dot products of block k+1 (env BH_COOP_FUSED)
+    // EXPERIMENT, rejected: skip the update sweep of a block whose coefficients are all < tau * beta.
+    // +8 % points/s at tau = 1e-13, but tau = 1e-12 breaks the 1e-10 parity at m=n=12 and 1e-14 the J = 0 recovery; keep 0.
+    double reorth_tau = 0.0;  // env BH_REORTH_TAU
+    int coop_fused = 1;    // cooperative step: update with block k fused with the dot products of block k+1 (env BH_COOP_FUSED)
     int coop = 1;          // single cooperative launch per Lanczos step when the residual fits in registers (env BH_COOP)
     int reorth_block = 8;  // basis columns per re-orthogonalisation block (env BH_REORTH_BLOCK)
     bool reorth_block_forced = false;

@@ -312,7 +312,7 @@ __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ p
 template <int CH>
 __global__ void __launch_bounds__(COOP_THREADS, 2)
 k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, int passes, const double* __restrict__ w,
-            double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused)
+            double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused, double tau)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[COOP_THREADS / 32][CH];
@@ -378,7 +378,8 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
     // ---- block modified Gram-Schmidt against columns 0..i ----
     double offd = b;
     int buf = 0;
-    // Fused form (BH_COOP_FUSED=1; measured slower at m=n=12, where two blocks of 8 columns exceed L2): the update with block k (its columns re-read from L2) and the dot products with block k+1
+    // Fused form (default; BH_COOP_FUSED=0 selects the two-sweep form below): the update with block k (its columns re-read
+    // from L2 with last-use loads, so that L2 drops them before the block being streamed in) and the dot products with block k+1
     // (streamed from HBM) run in the same sweep over the rows, so the two memory levels are busy together instead of in
     // turn; same arithmetic, same order of operations per row, one grid.sync per block as before.
     if (fused) {
@@ -427,8 +428,19 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                 double c[CH];
 #pragma unroll
                 for (int j = 0; j < CH; ++j) c[j] = cs[j];
-                if (i >= c0 && i < c0 + CH) alpha += cs[i - c0];                         // Lanczos.h:170
-                if (subtract && i - 1 >= c0 && i - 1 < c0 + CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
+                // Coefficients below tau * beta change no bit pattern that matters (tau = 0: always update): the update sweep
+                // of such a block (a full re-read of its columns) is skipped; the decision is the same in every CTA.
+                bool apply = true;
+                if (tau > 0.0 && subtract && passes == 1) {
+                    double cmax = 0.0;
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) cmax = fmax(cmax, fabs(c[j]));
+                    apply = !(cmax < tau * fabs(b));
+                }
+                if (apply) {
+                    if (i >= c0 && i < c0 + CH) alpha += cs[i - c0];                         // Lanczos.h:170
+                    if (subtract && i - 1 >= c0 && i - 1 < c0 + CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
+                }
                 // update with block c0, dot products with block c0 + CH
                 const int c1 = c0 + CH;
                 const int nc1 = (c1 <= i) ? min(CH, i + 1 - c1) : 0;
@@ -441,12 +453,15 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                     const int64_t p = gtid + t * gsz;
                     if (p < npair) {
                         double2 v[CH];
+                        if (apply) {
+                            // last use of block c0 in this step: let L2 drop these lines first, block c0 + CH has to stay
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
+                            for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? __ldlu(VB + (int64_t)j * ld2 + p) : make_double2(0.0, 0.0);
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            fr[t].x = fma(-v[j].x, c[j], fr[t].x);
-                            fr[t].y = fma(-v[j].y, c[j], fr[t].y);
+                            for (int j = 0; j < CH; ++j) {
+                                fr[t].x = fma(-v[j].x, c[j], fr[t].x);
+                                fr[t].y = fma(-v[j].y, c[j], fr[t].y);
+                            }
                         }
                         if (nc1 > 0) {
 #pragma unroll
@@ -947,7 +962,8 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
                 double* fv = ctx->d_f;
                 double th = near0;
                 int fused = ctx->coop_fused;
-                void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused};
+                double tau = ctx->reorth_tau;
+                void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused, &tau};
                 BH_CUDA(ctx, cudaLaunchCooperativeKernel(ctx->coop_ch == 4 ? (void*)k_step_coop<4> : (void*)k_step_coop<GT_CH>, dim3(coop_grid),
                                                      dim3(COOP_THREADS), args, 0, st));
                 BH_LAUNCHED(ctx);
