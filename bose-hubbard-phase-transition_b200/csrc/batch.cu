@@ -282,20 +282,32 @@ static int apply_single(bh_ctx* parent, bh_batch_hub* hub, int f)
 // alone) and un-park them.  Returns the first parked fiber (or -1) in *first.
 static int launch_parked(bh_ctx* parent, bh_batch_hub* hub, int* first)
 {
-    int fib[BH_MAX_BATCH], nf = 0;
+    int all[BH_MAX_BATCH], na = 0;
     for (int j = 0; j < hub->nfib; ++j)
-        if (!hub->done[j] && hub->parked[j]) fib[nf++] = j;
-    *first = nf ? fib[0] : -1;
-    int pos = 0, rc = BH_OK;
-    while (nf - pos >= 2 && rc == BH_OK) {
-        const int nb = (nf - pos >= 4) ? 4 : 2;
-        rc = apply_filters(parent, hub, fib + pos, nb);
-        pos += nb;
+        if (!hub->done[j] && hub->parked[j]) all[na++] = j;
+    *first = na ? all[0] : -1;
+    int rc = BH_OK;
+    // requests of the same polynomial degree go together (d = 1: a plain H.v of stage 1 / stage 3; d = the filter degree)
+    bool taken[BH_MAX_BATCH] = {false, false, false, false};
+    for (int a0 = 0; a0 < na && rc == BH_OK; ++a0) {
+        if (taken[a0]) continue;
+        int fib[BH_MAX_BATCH], nf = 0;
+        for (int a1 = a0; a1 < na; ++a1)
+            if (!taken[a1] && hub->req[all[a1]].d == hub->req[all[a0]].d) {
+                fib[nf++] = all[a1];
+                taken[a1] = true;
+            }
+        int pos = 0;
+        while (nf - pos >= 2 && rc == BH_OK) {
+            const int nb = (nf - pos >= 4) ? 4 : 2;
+            rc = apply_filters(parent, hub, fib + pos, nb);
+            pos += nb;
+        }
+        if (rc == BH_OK && pos < nf) rc = apply_single(parent, hub, fib[pos]);
     }
-    if (rc == BH_OK && pos < nf) rc = apply_single(parent, hub, fib[pos]);
-    for (int j = 0; j < nf; ++j) {
-        hub->req[fib[j]].rc = rc;
-        hub->parked[fib[j]] = false;
+    for (int j = 0; j < na; ++j) {
+        hub->req[all[j]].rc = rc;
+        hub->parked[all[j]] = false;
     }
     return rc;
 }

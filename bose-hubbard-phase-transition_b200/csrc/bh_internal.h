@@ -45,6 +45,7 @@ struct bh_ctx {
 
     // lockstep batching of grid points (batch.cu): bh_points solves `batch` points together, sharing their H.v launches
     int batch = 1;                       // env BH_BATCH / bh_ctx_set_batch (1 = off, 2..4)
+    int batch_plain = 0;                 // 1: the plain H.v of stage 1 / stage 3 go through the lockstep hub too (env BH_BATCH_PLAIN; measured slower: it fragments the filter batches)
     struct bh_batch_hub* hub = nullptr;  // parent side: scheduling state + interleaved buffers
     std::vector<bh_ctx*> children;       // parent side: one workspace-owning context per lockstep solve
     bh_ctx* parent = nullptr;            // child side

@@ -61,6 +61,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
     if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
     if (const char* v = getenv("BH_BATCH")) ctx->batch = std::min(4, std::max(1, atoi(v)));
+    if (const char* v = getenv("BH_BATCH_PLAIN")) ctx->batch_plain = atoi(v);
     if (const char* v = getenv("BH_SPLIT_G")) ctx->split_G = atoi(v);
     if (const char* v = getenv("BH_SPLIT_P")) ctx->split_p = atoi(v);
     if (const char* v = getenv("BH_SPLIT_UJ")) ctx->split_UJ = atoi(v);

@@ -1106,6 +1106,12 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
     int hv_count = 0;
     LanczosOp plain = [&](const double* x, double* y) {
         ++hv_count;
+        if (ctx->parent && ctx->parent->hub && ctx->parent->batch_plain) {
+            // lockstep solve: a plain H.v is a filter request of degree 1 with c = 0, e = 1 (s1 = 1, s2 = -0 is skipped)
+            bool handled = false;
+            BH_TRY(bh_batch_filter(ctx, x, y, 0.0, 1.0, cJ, cU, cmu, 1, &handled));
+            if (handled) return (int)BH_OK;
+        }
         return bh_launch_hv(ctx, cJ, cU, cmu, kernel, x, y);
     };
     const int d = ctx->cheb_degree;
