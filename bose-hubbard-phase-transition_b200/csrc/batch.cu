@@ -11,16 +11,15 @@
 // (12 cache lines per warp instruction, profiles/), which the interleaving amortises over the batch.
 // Per point the arithmetic is the same sequence of operations as the single-point kernel: results are bit-identical.
 #include <chrono>
-#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
-#include <mutex>
 #include <cstring>
 #include <thread>
 #include <vector>
 
 #include "bh_internal.h"
 #include "device_utils.cuh"
+#include "lockstep_sched.h"
 
 #define BH_MAX_BATCH 4
 
@@ -29,16 +28,10 @@ struct BatchReq {
     double* y = nullptr;
     double c = 0, e = 0, cJ = 0, cU = 0, cmu = 0;
     int d = 0;
-    int rc = BH_OK;
 };
 
 struct bh_batch_hub {
-    std::mutex mu;
-    std::condition_variable cv;
-    int nfib = 0;
-    int turn = -1;  // fiber allowed to run
-    bool done[BH_MAX_BATCH] = {false, false, false, false};
-    bool parked[BH_MAX_BATCH] = {false, false, false, false};
+    LockstepSched sched;  // who runs, who is parked (lockstep_sched.h)
     BatchReq req[BH_MAX_BATCH];
     double* d_il[3] = {nullptr, nullptr, nullptr};  // interleaved Chebyshev buffers, ld * BH_MAX_BATCH doubles each
     int64_t il_len = 0;
@@ -240,16 +233,7 @@ static int apply_filters(bh_ctx* parent, bh_batch_hub* hub, const int* fib, int 
     return BH_OK;
 }
 
-// ---- fiber scheduling: exactly one fiber runs at any time ----
-static int next_runnable(bh_batch_hub* hub, int after)
-{
-    for (int o = 1; o <= hub->nfib; ++o) {
-        const int j = (after + o) % hub->nfib;
-        if (!hub->done[j] && !hub->parked[j]) return j;
-    }
-    return -1;
-}
-
+// ---- what a launch does for a group of parked solves with the same degree ----
 // One parked fiber alone: its filter through the ordinary single-vector kernel on its own buffers.
 static int apply_single(bh_ctx* parent, bh_batch_hub* hub, int f)
 {
@@ -278,37 +262,17 @@ static int apply_single(bh_ctx* parent, bh_batch_hub* hub, int f)
     return rc;
 }
 
-// With hub->mu held and no runnable fiber left: apply the filters of every parked fiber (quadruples, pairs, a leftover
-// alone) and un-park them.  Returns the first parked fiber (or -1) in *first.
-static int launch_parked(bh_ctx* parent, bh_batch_hub* hub, int* first)
+// Launch callback of the scheduler: the parked solves grp[0..ng) asked for the same degree; quadruples and pairs share
+// their launches, a leftover runs alone.  Called with the scheduler lock held, by the thread that holds the baton.
+static int launch_group(bh_ctx* parent, bh_batch_hub* hub, const int* grp, int ng)
 {
-    int all[BH_MAX_BATCH], na = 0;
-    for (int j = 0; j < hub->nfib; ++j)
-        if (!hub->done[j] && hub->parked[j]) all[na++] = j;
-    *first = na ? all[0] : -1;
-    int rc = BH_OK;
-    // requests of the same polynomial degree go together (d = 1: a plain H.v of stage 1 / stage 3; d = the filter degree)
-    bool taken[BH_MAX_BATCH] = {false, false, false, false};
-    for (int a0 = 0; a0 < na && rc == BH_OK; ++a0) {
-        if (taken[a0]) continue;
-        int fib[BH_MAX_BATCH], nf = 0;
-        for (int a1 = a0; a1 < na; ++a1)
-            if (!taken[a1] && hub->req[all[a1]].d == hub->req[all[a0]].d) {
-                fib[nf++] = all[a1];
-                taken[a1] = true;
-            }
-        int pos = 0;
-        while (nf - pos >= 2 && rc == BH_OK) {
-            const int nb = (nf - pos >= 4) ? 4 : 2;
-            rc = apply_filters(parent, hub, fib + pos, nb);
-            pos += nb;
-        }
-        if (rc == BH_OK && pos < nf) rc = apply_single(parent, hub, fib[pos]);
+    int pos = 0, rc = BH_OK;
+    while (ng - pos >= 2 && rc == BH_OK) {
+        const int nb = (ng - pos >= 4) ? 4 : 2;
+        rc = apply_filters(parent, hub, grp + pos, nb);
+        pos += nb;
     }
-    for (int j = 0; j < na; ++j) {
-        hub->req[all[j]].rc = rc;
-        hub->parked[all[j]] = false;
-    }
+    if (rc == BH_OK && pos < ng) rc = apply_single(parent, hub, grp[pos]);
     return rc;
 }
 
@@ -321,29 +285,13 @@ int bh_batch_filter(bh_ctx* child, const double* x, double* y, double c, double 
     bh_ctx* parent = child->parent;
     bh_batch_hub* hub = parent->hub;
     const int me = child->fiber;
-    std::unique_lock<std::mutex> lk(hub->mu);
-    int live = 0;
-    for (int j = 0; j < hub->nfib; ++j) live += hub->done[j] ? 0 : 1;
-    if (live < 2) {
-        *handled = false;
-        hub->single_filters++;
-        return BH_OK;
-    }
-    *handled = true;
+    // the request record is read by the launching thread only after this fiber has parked (under the scheduler lock)
     BatchReq& r = hub->req[me];
-    r.x = x; r.y = y; r.c = c; r.e = e; r.cJ = cJ; r.cU = cU; r.cmu = cmu; r.d = d; r.rc = BH_OK;
-    hub->parked[me] = true;
-    const int nxt = next_runnable(hub, me);
-    if (nxt >= 0) {
-        // another solve still has host work to do before its filter: hand the baton over and wait to be un-parked
-        hub->turn = nxt;
-        hub->cv.notify_all();
-        hub->cv.wait(lk, [&] { return hub->turn == me && !hub->parked[me]; });
-        return hub->req[me].rc;
-    }
-    // every live solve is parked: this thread launches for all of them and keeps the baton
-    int first = -1;
-    return launch_parked(parent, hub, &first);
+    r.x = x; r.y = y; r.c = c; r.e = e; r.cJ = cJ; r.cU = cU; r.cmu = cmu; r.d = d;
+    int status = BH_OK;
+    *handled = hub->sched.request(me, d, [&](const int* grp, int ng) { return launch_group(parent, hub, grp, ng); }, &status);
+    if (!*handled) hub->single_filters++;
+    return status;
 }
 
 void bh_batch_release(bh_ctx* ctx)
@@ -410,9 +358,7 @@ int bh_points_lockstep(bh_ctx* ctx, int nb, int64_t npoints, const double* cJ, c
     BH_TRY(ensure_children(ctx, nb));
     const auto t_children = std::chrono::steady_clock::now();
     bh_batch_hub* hub = ctx->hub;
-    hub->nfib = nb;
-    hub->turn = 0;
-    for (int j = 0; j < BH_MAX_BATCH; ++j) hub->done[j] = hub->parked[j] = false;
+    hub->sched.reset(nb);
     int rcs[BH_MAX_BATCH] = {BH_OK, BH_OK, BH_OK, BH_OK};
     int64_t next_point = 0;  // guarded by the baton (only the running fiber touches it)
     bool stop = false;
@@ -422,10 +368,7 @@ int bh_points_lockstep(bh_ctx* ctx, int nb, int64_t npoints, const double* cJ, c
         c->stream = ctx->stream;
         c->cheb_degree = ctx->cheb_degree;
         threads.emplace_back([=, &rcs, &next_point, &stop] {
-            {
-                std::unique_lock<std::mutex> lk(hub->mu);
-                hub->cv.wait(lk, [&] { return hub->turn == i; });
-            }
+            hub->sched.wait_first_turn(i);
             for (;;) {
                 if (stop || next_point >= npoints) break;
                 const int64_t p = next_point++;
@@ -440,13 +383,8 @@ int bh_points_lockstep(bh_ctx* ctx, int nb, int64_t npoints, const double* cJ, c
                     stop = true;
                 }
             }
-            // leave: pass the baton; if every remaining live solve is parked, launch their filters first
-            std::unique_lock<std::mutex> lk(hub->mu);
-            hub->done[i] = true;
-            int nxt = next_runnable(hub, i);
-            if (nxt < 0) launch_parked(ctx, hub, &nxt);
-            hub->turn = nxt;
-            hub->cv.notify_all();
+            // leave: pass the baton; if every remaining live solve is parked, their filters are launched first
+            hub->sched.finish(i, [&](const int* grp, int ng) { return launch_group(ctx, hub, grp, ng); });
         });
     }
     for (auto& t : threads) t.join();

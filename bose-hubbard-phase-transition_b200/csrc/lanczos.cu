@@ -312,7 +312,7 @@ __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ p
 template <int CH>
 __global__ void __launch_bounds__(COOP_THREADS, 2)
 k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, int passes, const double* __restrict__ w,
-            double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused, double tau)
+            double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused, double tau, int pf)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[COOP_THREADS / 32][CH];
@@ -416,6 +416,19 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                     double t = 0.0;
                     for (int q = 0; q < COOP_THREADS / 32; ++q) t += red[q][threadIdx.x];
                     pc[(int64_t)blockIdx.x * CH + threadIdx.x] = t;
+                }
+                if (pf > 0 && c0 + CH <= i) {
+                    // the sweep after the barrier starts with first-touch (HBM) loads of block c0 + CH: start them now so
+                    // that the barrier and the reduction hide their latency (one request per 128-byte line, no registers)
+                    const int ncp = min(CH, i + 1 - (c0 + CH));
+                    const double2* VP = V2 + (int64_t)(c0 + CH) * ld2;
+                    if ((lane & 7) == 0) {
+                        for (int t = 0; t < pf; ++t) {
+                            const int64_t p = gtid + t * gsz;
+                            if (p < npair)
+                                for (int j = 0; j < ncp; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(VP + (int64_t)j * ld2 + p));
+                        }
+                    }
                 }
                 grid.sync();
                 if (wid < nc) {
@@ -963,7 +976,8 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
                 double th = near0;
                 int fused = ctx->coop_fused;
                 double tau = ctx->reorth_tau;
-                void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused, &tau};
+                int pf = ctx->coop_prefetch;
+                void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused, &tau, &pf};
                 BH_CUDA(ctx, cudaLaunchCooperativeKernel(ctx->coop_ch == 4 ? (void*)k_step_coop<4> : (void*)k_step_coop<GT_CH>, dim3(coop_grid),
                                                      dim3(COOP_THREADS), args, 0, st));
                 BH_LAUNCHED(ctx);
