@@ -120,6 +120,7 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
         if (!ok) partial << hdr.str() << std::endl;
         partial << std::setprecision(17);
     }
+    const int kernel = opt.kernel >= 0 ? opt.kernel : (opt.lx > 0 ? BH_HV_STORED : BH_HV_MATRIX_FREE);
     const bool shift_rows = opt.reuse_shift && g.fixed != "u";
     const int ntasks = shift_rows ? g.num1 : total;
     while (true) {
@@ -153,8 +154,8 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
                         ts[nt++] = t;
                     }
                     if (nt == 0) break;
-                    const int rc = nt == 1 ? bh_point(ctxs[d], cJ[0], cU[0], cmu[0], nb_eigen, opt.kernel, out3, nullptr, nullptr, nullptr)
-                                           : bh_points(ctxs[d], cJ, cU, cmu, nt, nb_eigen, opt.kernel, out3, nullptr);
+                    const int rc = nt == 1 ? bh_point(ctxs[d], cJ[0], cU[0], cmu[0], nb_eigen, kernel, out3, nullptr, nullptr, nullptr)
+                                           : bh_points(ctxs[d], cJ, cU, cmu, nt, nb_eigen, kernel, out3, nullptr);
                     if (rc == BH_ERR_ARG) throw std::invalid_argument(bh_last_error(ctxs[d]));
                     if (rc != BH_OK) throw std::runtime_error(bh_last_error(ctxs[d]));
                     std::lock_guard<std::mutex> lk(mtx);

@@ -13,7 +13,7 @@ struct ExactOptions {
     bool resume = false;           // append finished points to <output>.partial and skip them when restarted
     bool reuse_shift = false;      // -f J / -f U: the second parameter only shifts the spectrum; solve each row once
     int contexts_per_gpu = 1;      // concurrent grid points per GPU (each on its own context)
-    int kernel = 0;                // BH_HV_STORED (0) or BH_HV_MATRIX_FREE (1)
+    int kernel = -1;               // BH_HV_STORED (0), BH_HV_MATRIX_FREE (1); -1 = matrix-free for chains (faster, lockstep-capable), stored for other lattices
     int batch = 4;                 // grid points solved in lockstep per context (bh_ctx_set_batch; effective for chains + matrix-free)
     int lx = 0, ly = 0, lz = 0;    // lx*ly*lz == m selects a periodic box; all zero = closed chain (reference)
     bool closed = true;

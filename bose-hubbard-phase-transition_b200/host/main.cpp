@@ -31,7 +31,7 @@ static void print_usage()
               << "  -e, --epsilon  Threshold for convergence in the mean-field approximation\n"
               << "  -g, --gpus      GPUs to shard the sweep over (default: all visible)\n"
               << "  -l, --lattice   chain (default) or LXxLY[xLZ] periodic box\n"
-              << "  -k, --kernel    stored (default) or free (matrix-free H.v)\n"
+              << "  -k, --kernel    stored or free (matrix-free H.v); default: free for chains, stored for --lattice\n"
               << "  -o, --output    Output file (default phase.txt)\n"
               << "  -c, --concurrent Grid points solved concurrently per GPU (default 1)\n"
               << "      --no-plot   Do not run plot.py afterwards\n"

@@ -100,10 +100,14 @@ CLI_RUNS = {
 }
 
 
+@pytest.mark.parametrize("extra", [(), ("--kernel", "stored"), ("--kernel", "free", "--batch", "1")],
+                         ids=["default-free-lockstep4", "stored", "free-single"])
 @pytest.mark.parametrize("name", sorted(CLI_RUNS))
-def test_cli_phase_txt(name):
+def test_cli_phase_txt(name, extra):
+    if extra and name in ("phase_m8_C1.txt", "phase_m10_fJ.txt"):
+        pytest.skip("the long sweeps run once, through the default path")
     with tempfile.TemporaryDirectory() as td:
-        p = subprocess.run([CLI] + [str(a) for a in CLI_RUNS[name]], cwd=td, capture_output=True, text=True, timeout=900)
+        p = subprocess.run([CLI] + [str(a) for a in CLI_RUNS[name]] + list(extra), cwd=td, capture_output=True, text=True, timeout=900)
         assert p.returncode == 0, (p.stdout[-500:], p.stderr[-500:])
         assert "Calculation duration:" in p.stdout and "Memory usage:" in p.stdout and "Progress: [" in p.stdout
         got = open(os.path.join(td, "phase.txt")).read()
