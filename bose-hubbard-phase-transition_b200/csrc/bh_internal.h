@@ -125,6 +125,7 @@ struct bh_ctx {
     // EXPERIMENT, rejected: skip the update sweep of a block whose coefficients are all < tau * beta.
     // +8 % points/s at tau = 1e-13, but tau = 1e-12 breaks the 1e-10 parity at m=n=12 and 1e-14 the J = 0 recovery; keep 0.
     double reorth_tau = 0.0;  // env BH_REORTH_TAU
+    int coop_smem = 0;      // cooperative step with the residual in shared memory, 3 CTAs per SM (env BH_COOP_SMEM)
     int coop_prefetch = 0;  // fused cooperative step: row chunks of the next block prefetched into L2 before each grid barrier (env BH_COOP_PREFETCH; measured slower: 2 -> -1 %, 10 -> -6 %)
     int coop_fused = 1;    // cooperative step: update with block k fused with the dot products of block k+1 (env BH_COOP_FUSED)
     int coop = 1;          // single cooperative launch per Lanczos step when the residual fits in registers (env BH_COOP)

@@ -72,6 +72,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
     if (const char* v = getenv("BH_COOP_FUSED")) ctx->coop_fused = atoi(v);
     if (const char* v = getenv("BH_RR_GRAM")) ctx->rr_gram = atoi(v);
+    if (const char* v = getenv("BH_COOP_SMEM")) ctx->coop_smem = atoi(v);
     if (const char* v = getenv("BH_COOP_PREFETCH")) ctx->coop_prefetch = std::max(0, std::min(10, atoi(v)));
     if (const char* v = getenv("BH_REORTH_TAU")) ctx->reorth_tau = atof(v);
     if (const char* v = getenv("BH_COOP_CH")) ctx->coop_ch = (atoi(v) == 4) ? 4 : 8;

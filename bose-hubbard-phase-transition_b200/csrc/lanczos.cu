@@ -299,6 +299,7 @@ __global__ void k_fin_coef(double* __restrict__ scal, int i, int pass)
 // All partial sums are combined in a fixed order (deterministic).
 // ---------------------------------------------------------------------------------------------------------
 #define COOP_NP 10
+#define COOP_NP_S 6  // row pairs per thread of the shared-memory-residual form (3 CTAs per SM)
 #define COOP_THREADS 256
 
 __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ part, int n, int stride)
@@ -309,8 +310,10 @@ __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ p
     return bh_warp_sum(t);
 }
 
-template <int CH>
-__global__ void __launch_bounds__(COOP_THREADS, 2)
+// NP = row pairs per thread; FRS = the residual lives in shared memory instead of registers (85 instead of 128 registers:
+// three CTAs per SM, 24 warps instead of 16 -- the kernel is latency-bound, profiles/r01_ncu_final_kernels.md)
+template <int CH, int NP, bool FRS>
+__global__ void __launch_bounds__(COOP_THREADS, (FRS ? 3 : 2))
 k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, int passes, const double* __restrict__ w,
             double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused, double tau, int pf)
 {
@@ -332,12 +335,14 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
 
     // ---- three-term update and alpha ----
     const double b = subtract ? scal[S_BETA + i] : 0.0;
-    double2 fr[COOP_NP];
+    extern __shared__ double2 s_fr[];  // [NP][COOP_THREADS] when FRS
+    double2 fr_reg[FRS ? 1 : NP];
+#define FR(t) (FRS ? s_fr[(t) * COOP_THREADS + threadIdx.x] : fr_reg[FRS ? 0 : (t)])
     double acc0 = 0.0;
 #pragma unroll
-    for (int t = 0; t < COOP_NP; ++t) {
+    for (int t = 0; t < NP; ++t) {
         const int64_t p = gtid + t * gsz;
-        fr[t] = make_double2(0.0, 0.0);
+        FR(t) = make_double2(0.0, 0.0);
         if (p < npair) {
             double2 wr = w2[p];
             if (subtract) {
@@ -347,7 +352,7 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
             }
             const double2 v = vi2[p];
             acc0 = fma(v.x, wr.x, fma(v.y, wr.y, acc0));
-            fr[t] = wr;
+            FR(t) = wr;
         }
     }
     acc0 = bh_warp_sum(acc0);
@@ -366,12 +371,12 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
     __syncthreads();
     double alpha = sh_val;
 #pragma unroll
-    for (int t = 0; t < COOP_NP; ++t) {
+    for (int t = 0; t < NP; ++t) {
         const int64_t p = gtid + t * gsz;
         if (p < npair) {
             const double2 v = vi2[p];
-            fr[t].x = fma(-alpha, v.x, fr[t].x);
-            fr[t].y = fma(-alpha, v.y, fr[t].y);
+            FR(t).x = fma(-alpha, v.x, FR(t).x);
+            FR(t).y = fma(-alpha, v.y, FR(t).y);
         }
     }
 
@@ -390,14 +395,14 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
             {
                 const int nc = min(CH, i + 1);
 #pragma unroll
-                for (int t = 0; t < COOP_NP; ++t) {
+                for (int t = 0; t < NP; ++t) {
                     const int64_t p = gtid + t * gsz;
                     if (p < npair) {
                         double2 v[CH];
 #pragma unroll
                         for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? V2[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
-                        for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
+                        for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, FR(t).x, fma(v[j].y, FR(t).y, acc[j]));
                     }
                 }
             }
@@ -462,7 +467,7 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
 #pragma unroll
                 for (int j = 0; j < CH; ++j) acc[j] = 0.0;
 #pragma unroll
-                for (int t = 0; t < COOP_NP; ++t) {
+                for (int t = 0; t < NP; ++t) {
                     const int64_t p = gtid + t * gsz;
                     if (p < npair) {
                         double2 v[CH];
@@ -472,15 +477,15 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                             for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? __ldlu(VB + (int64_t)j * ld2 + p) : make_double2(0.0, 0.0);
 #pragma unroll
                             for (int j = 0; j < CH; ++j) {
-                                fr[t].x = fma(-v[j].x, c[j], fr[t].x);
-                                fr[t].y = fma(-v[j].y, c[j], fr[t].y);
+                                FR(t).x = fma(-v[j].x, c[j], FR(t).x);
+                                FR(t).y = fma(-v[j].y, c[j], FR(t).y);
                             }
                         }
                         if (nc1 > 0) {
 #pragma unroll
                             for (int j = 0; j < CH; ++j) v[j] = (j < nc1) ? VN[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
+                            for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, FR(t).x, fma(v[j].y, FR(t).y, acc[j]));
                         }
                     }
                 }
@@ -497,14 +502,14 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
 #pragma unroll
             for (int j = 0; j < CH; ++j) acc[j] = 0.0;
 #pragma unroll
-            for (int t = 0; t < COOP_NP; ++t) {
+            for (int t = 0; t < NP; ++t) {
                 const int64_t p = gtid + t * gsz;
                 if (p < npair) {
                     double2 v[CH];
 #pragma unroll
                     for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
-                    for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, fr[t].x, fma(v[j].y, fr[t].y, acc[j]));
+                    for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, FR(t).x, fma(v[j].y, FR(t).y, acc[j]));
                 }
             }
 #pragma unroll
@@ -534,7 +539,7 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
             if (i >= c0 && i < c0 + CH) alpha += cs[i - c0];                         // Lanczos.h:170
             if (subtract && i - 1 >= c0 && i - 1 < c0 + CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
 #pragma unroll
-            for (int t = 0; t < COOP_NP; ++t) {
+            for (int t = 0; t < NP; ++t) {
                 const int64_t p = gtid + t * gsz;
                 if (p < npair) {
                     double2 v[CH];
@@ -542,8 +547,8 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                     for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? VB[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
                     for (int j = 0; j < CH; ++j) {
-                        fr[t].x = fma(-v[j].x, c[j], fr[t].x);
-                        fr[t].y = fma(-v[j].y, c[j], fr[t].y);
+                        FR(t).x = fma(-v[j].x, c[j], FR(t).x);
+                        FR(t).y = fma(-v[j].y, c[j], FR(t).y);
                     }
                 }
             }
@@ -555,7 +560,7 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
     // ---- norm, write-back, next basis vector ----
     double nrm = 0.0;
 #pragma unroll
-    for (int t = 0; t < COOP_NP; ++t) nrm = fma(fr[t].x, fr[t].x, fma(fr[t].y, fr[t].y, nrm));
+    for (int t = 0; t < NP; ++t) nrm = fma(FR(t).x, FR(t).x, fma(FR(t).y, FR(t).y, nrm));
     nrm = bh_warp_sum(nrm);
     if (lane == 0) red[wid][0] = nrm;
     __syncthreads();
@@ -575,11 +580,11 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
     double2* f2 = reinterpret_cast<double2*>(f);
     double2* vn2 = reinterpret_cast<double2*>(V + (int64_t)(i + 1) * ld);
 #pragma unroll
-    for (int t = 0; t < COOP_NP; ++t) {
+    for (int t = 0; t < NP; ++t) {
         const int64_t p = gtid + t * gsz;
         if (p < npair) {
-            f2[p] = fr[t];
-            vn2[p] = make_double2(fr[t].x * inv, fr[t].y * inv);
+            f2[p] = FR(t);
+            vn2[p] = make_double2(FR(t).x * inv, FR(t).y * inv);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -592,6 +597,7 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
         }
     }
 }
+#undef FR
 
 // x *= 1 / scal[idx]  (final normalisation of a Ritz vector: under partial re-orthogonalisation the basis is
 // orthonormal only to sqrt(eps), so |V y| differs from 1 at that level)
@@ -921,15 +927,27 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
 
     // cooperative single-launch step: needs every CTA resident and <= COOP_NP row pairs per thread
     int coop_grid = 0;
+    bool coop_smem = false;
     if (ctx->coop && !dist) {
         int bps = 0;
-        if (ctx->coop_ch == 4)
-            BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<4>, COOP_THREADS, 0));
-        else
-            BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH>, COOP_THREADS, 0));
-        bps = std::min(bps, 2);
         const int64_t npair = (D + 1) / 2;
-        if (bps >= 1 && npair <= (int64_t)ctx->sm_count * bps * COOP_THREADS * COOP_NP) {
+        // residual in shared memory (3 CTAs per SM, COOP_NP_S pairs per thread) when it fits; else the register form
+        coop_smem = ctx->coop_smem && ctx->coop_ch != 4;
+        if (coop_smem) {
+            BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH, COOP_NP_S, true>, COOP_THREADS,
+                                                                        sizeof(double2) * COOP_NP_S * COOP_THREADS));
+            bps = std::min(bps, 3);
+            if (bps < 3 || npair > (int64_t)ctx->sm_count * bps * COOP_THREADS * COOP_NP_S) coop_smem = false;
+        }
+        if (!coop_smem) {
+            if (ctx->coop_ch == 4)
+                BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<4, COOP_NP, false>, COOP_THREADS, 0));
+            else
+                BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH, COOP_NP, false>, COOP_THREADS, 0));
+            bps = std::min(bps, 2);
+        }
+        const int coop_np = coop_smem ? COOP_NP_S : COOP_NP;
+        if (bps >= 1 && npair <= (int64_t)ctx->sm_count * bps * COOP_THREADS * coop_np) {
             coop_grid = ctx->sm_count * bps;
             // do not spread a tiny problem over idle CTAs: grid syncs cost more with more CTAs
             const int64_t need = (npair + COOP_THREADS - 1) / COOP_THREADS;
@@ -978,8 +996,10 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
                 double tau = ctx->reorth_tau;
                 int pf = ctx->coop_prefetch;
                 void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused, &tau, &pf};
-                BH_CUDA(ctx, cudaLaunchCooperativeKernel(ctx->coop_ch == 4 ? (void*)k_step_coop<4> : (void*)k_step_coop<GT_CH>, dim3(coop_grid),
-                                                     dim3(COOP_THREADS), args, 0, st));
+                void* fn = coop_smem ? (void*)k_step_coop<GT_CH, COOP_NP_S, true>
+                                     : (ctx->coop_ch == 4 ? (void*)k_step_coop<4, COOP_NP, false> : (void*)k_step_coop<GT_CH, COOP_NP, false>);
+                const size_t fr_bytes = coop_smem ? sizeof(double2) * COOP_NP_S * COOP_THREADS : 0;
+                BH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(coop_grid), dim3(COOP_THREADS), args, fr_bytes, st));
                 BH_LAUNCHED(ctx);
                 continue;
             }
