@@ -50,15 +50,23 @@ def needs_more_eigenvalues(gap_ratios):
     return not (var > 1e-8 * mean)
 
 
-def run_sweep(point_fn, grid, world=1, rank=0, dist=None, nb_eigen=20):
+def run_sweep(point_fn, grid, world=1, rank=0, dist=None, nb_eigen=20, points_fn=None, chunk=16):
     """point_fn(cJ, cU, cmu, nb_eigen) -> (gap_ratio, condensate_fraction, coherence) for the local shard;
-    results are exchanged once at the end (all_gather of 3 doubles per point).  Returns the rows of phase.txt."""
+    results are exchanged once at the end (all_gather of 3 doubles per point).  Returns the rows of phase.txt.
+    points_fn(cJ[], cU[], cmu[], nb_eigen) -> array[n, 3], when given, evaluates the shard in chunks of `chunk` points
+    (bh_points: the points of a chunk are solved in lockstep and share their H.v launches; same results)."""
     pts = grid["points"]
     total = grid["num1"] * grid["num2"]
     while True:
         mine = shard(len(pts), world, rank)
         local = np.zeros((len(mine), 4))
-        for k, t in enumerate(mine):
+        if points_fn is not None:
+            for k0 in range(0, len(mine), max(1, chunk)):
+                sel = mine[k0:k0 + max(1, chunk)]
+                c = np.array([pts[t][3:6] for t in sel], dtype=np.float64).reshape(len(sel), 3)
+                local[k0:k0 + len(sel), 0] = sel
+                local[k0:k0 + len(sel), 1:] = np.asarray(points_fn(c[:, 0].copy(), c[:, 1].copy(), c[:, 2].copy(), nb_eigen)).reshape(len(sel), 3)
+        for k, t in enumerate(mine if points_fn is None else []):
             _, _, _, cJ, cU, cmu = pts[t]
             local[k, 0] = t
             local[k, 1:] = point_fn(cJ, cU, cmu, nb_eigen)

@@ -52,13 +52,28 @@ def fake_point(cJ, cU, cmu, nb):
     return (np.sin(cJ + 2 * cU) ** 2, 0.5 + 0.01 * cU, 0.25 * cJ + 0.125 * cmu)
 
 
+def fake_points(cJ, cU, cmu, nb):
+    return np.array([fake_point(a, b, c, nb) for a, b, c in zip(cJ, cU, cmu)])
+
+
+def test_chunked_evaluation_equals_point_by_point():
+    sw = sweep_mod()
+    g = sw.make_grid("J", 1, 0, 0, 4, 1)
+    serial = sw.run_sweep(fake_point, g)
+    for chunk in (1, 3, 16, 100):
+        assert np.array_equal(sw.run_sweep(fake_point, g, points_fn=fake_points, chunk=chunk), serial)
+    for world in (2, 3):   # the shards of every rank, evaluated in chunks, cover the grid exactly once
+        seen = sorted(t for r in range(world) for t in sw.shard(len(g["points"]), world, r))
+        assert seen == list(range(len(g["points"])))
+
+
 def worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sw = sweep_mod()
     g = sw.make_grid("J", 1, 0, 0, 4, 1)
-    rows = sw.run_sweep(fake_point, g, world, rank, dist)
+    rows = sw.run_sweep(fake_point, g, world, rank, dist, points_fn=fake_points if rank == 0 else None, chunk=4)
     q.put((rank, rows))
     dist.destroy_process_group()
 
