@@ -21,7 +21,7 @@ void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::
     std::vector<double> q((size_t)n * n, 0.0);
     auto Q = [&](int i, int j) -> double& { return q[i + (size_t)j * n]; };
     for (int i = 0; i < n; ++i) Q(i, i) = 1.0;
-    std::vector<double> v(n), p(n);
+    std::vector<double> v(n), p(n), t(n);
 
     // ---- Householder tridiagonalisation, column by column ----
     for (int k = 0; k + 2 < n; ++k) {
@@ -43,7 +43,8 @@ void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::
         double K = 0;
         for (int i = k + 1; i < n; ++i) {
             double s = 0;
-            for (int j = k + 1; j < n; ++j) s += A(i, j) * v[j];
+            const double* col = &A(0, i);  // A is symmetric: row i = column i, contiguous
+            for (int j = k + 1; j < n; ++j) s += col[j] * v[j];
             p[i] = s;
             K += s * v[i];
         }
@@ -52,12 +53,17 @@ void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::
             for (int i = k + 1; i < n; ++i) A(i, j) -= 2.0 * (v[i] * p[j] + p[i] * v[j]);
         A(k + 1, k) = A(k, k + 1) = alpha;
         for (int i = k + 2; i < n; ++i) A(i, k) = A(k, i) = 0.0;
-        // Q <- Q (I - 2 v v^T)
-        for (int i = 0; i < n; ++i) {
-            double s = 0;
-            for (int j = k + 1; j < n; ++j) s += Q(i, j) * v[j];
-            s *= 2.0;
-            for (int j = k + 1; j < n; ++j) Q(i, j) -= s * v[j];
+        // Q <- Q (I - 2 v v^T), column by column (contiguous): t = 2 Q v, then Q(:, j) -= t v_j
+        std::fill(t.begin(), t.end(), 0.0);
+        for (int j = k + 1; j < n; ++j) {
+            const double vj = 2.0 * v[j];
+            const double* col = &Q(0, j);
+            for (int i = 0; i < n; ++i) t[i] += col[i] * vj;
+        }
+        for (int j = k + 1; j < n; ++j) {
+            const double vj = v[j];
+            double* col = &Q(0, j);
+            for (int i = 0; i < n; ++i) col[i] -= t[i] * vj;
         }
     }
     std::vector<double> d(n), e(std::max(n - 1, 0));
@@ -84,7 +90,7 @@ void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::
         const double mu = d[hi] - eh * eh / den;
         double x = d[lo] - mu, z = e[lo];
         for (int k = lo; k < hi; ++k) {
-            const double r = std::hypot(x, z);
+            const double r = std::sqrt(x * x + z * z);  // entries are O(|T|): no overflow guard needed (std::hypot costs more than the rotation)
             const double c = (r == 0) ? 1.0 : x / r;
             const double s = (r == 0) ? 0.0 : -z / r;
             if (k > lo) e[k - 1] = r;
@@ -97,10 +103,12 @@ void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::
                 z = -s * e[k + 1];
                 e[k + 1] = c * e[k + 1];
             }
+            double* __restrict__ q0 = &Q(0, k);
+            double* __restrict__ q1 = &Q(0, k + 1);
             for (int i = 0; i < n; ++i) {
-                const double qk = Q(i, k), qk1 = Q(i, k + 1);
-                Q(i, k) = c * qk - s * qk1;
-                Q(i, k + 1) = s * qk + c * qk1;
+                const double qk = q0[i], qk1 = q1[i];
+                q0[i] = c * qk - s * qk1;
+                q1[i] = s * qk + c * qk1;
             }
         }
     }
