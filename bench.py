@@ -6,20 +6,23 @@
 Workload (config 3 of BASELINE.json, SURVEY.md section 8d "C3"): closed chain m = 12 sites, n = 12 bosons
 (D = 1 352 078, nnz(H) = 18 282 446), the 32 x 32 grid of `-J 1 -U 0 -u 0 -r 31 -s 1 -f J`
 (J-coefficient 1, U-coefficient 1..32, mu 0..31).  A step = one list of P (default 8) grid points per GPU (eigensolve for
-the 20 lowest levels + gap ratio + SPDM + condensate fraction + coherence; the points of a batch are solved in lockstep and
+the 20 lowest levels + gap ratio + SPDM + condensate fraction + coherence; the points of a list are solved in lockstep and
 share their H.v launches, --batch, results identical point by point); every rank gets the same U values (a fixed
 pseudo-random order over the grid's 32) at different mu; per-GPU work is fixed as N grows (weak scaling, no data-path
 collective).
 
-  value     points/s, whole job, basis + stored H resident in HBM, timed with CUDA events on the launching stream
-  e2e       points/s through the C ABI from a cold context: bh_setup + bh_points with host buffers, wall clock,
-            PCIe bytes counted by the library (bh_ctx_transfer_bytes)
-  roofline  the stored-CSR H.v kernel (K3) timed alone with CUDA events: algorithmic bytes / duration vs the
-            measured HBM copy peak (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference
-            the (patched) reference's own solver call on the host cores: `nproc` concurrent copies of one C3 point,
-            each stopped after a bounded number of restarts (a full C3 point takes ~4 min per core), points/s
-            extrapolated by the H.v-count ratio to the converged solve
+  value          points/s, whole job, basis resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e            points/s through the C ABI from a cold context: bh_setup + bh_points with host buffers, wall clock, PCIe
+                 bytes counted by the library; its results must equal the timed region's bit for bit (asserted)
+  roofline       the kernel class with the largest share of the step, timed with CUDA event pairs around every launch
+                 (bh_ctx_profile_*) in a pass over the same grid points right after the timed region
+  roofline_path  the same for every kernel class of the step + the stored H.v (k_hv_sell) alone, warm and cold
+  stored_kernel  points/s of the same step with the stored SELL-32 H.v (BASELINE.json words C3 as "stored-CSR Lanczos")
+  small_configs  C1 / C2 (m = n = 8 / 10, the full 11 x 11 grids) points/s through the same call
+  c5             N = 1: matrix-free H.v and the nev = 2 solve at m = n = 14; N > 1: the row-partitioned solve with --check
+  cpu_baseline   the compiled reference's own solver call on the host cores, bounded sample (N = 1 only)
+
+--impl reference: the compiled (patched) reference on the host cores; K + W bounded steps + one fully converged batch.
 """
 import argparse
 import json
@@ -36,13 +39,24 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 GRID = 32  # -r 31 -s 1  ->  int(31 / 1) + 1 points per axis
-# H.v applications of the REFERENCE algorithm (Spectra, nev 20, ncv 41) per converged C3 point, mean over the 32 U values
-# of the grid: measured with this library's plain mode (BH_CHEB_DEGREE=1), whose counts track Spectra's within a few %
-# (DESIGN.md section 4); used only to scale the bounded CPU sample to a full solve.
-REF_MEAN_MATVECS = 2167
+# identical in both arms (the driver compares the dicts)
+CONFIG = {"workload": "C3: closed chain m=12 n=12 (D=1352078, nnz(H)=18282446), 32x32 grid of -J 1 -U 0 -u 0 -r 31 -s 1 -f J",
+          "m": 12, "n": 12, "nev": 20, "ncv": 41, "tol": 1e-10,
+          "l2": "inputs larger than L2 (Krylov basis 454 MB per point in flight; stored H 433 MB)"}
+KERNEL_NAMES = {
+    "hv_free": "k_hv_free_chain<12> (matrix-free H.v, one vector)",
+    "hv_batch2": "k_hv_chain_batch<12,2> (matrix-free H.v, 2 lockstep vectors)",
+    "hv_batch4": "k_hv_chain_batch<12,4> (matrix-free H.v, 4 lockstep vectors)",
+    "hv_stored": "k_hv_sell (stored H.v, SELL-32)",
+    "step": "k_step_coop<8> (Lanczos step: three-term update + full re-orthogonalisation + normalisation)",
+    "restart": "k_compress_tiled8 (thick restart V <- V Y)",
+    "gram": "k_gram (Rayleigh-Ritz Gram pass)",
+    "spdm": "k_spdm<12> (single-particle density matrix)",
+    "small": "k_small_* (many-point small-system solver)",
+}
 
 
-def grid_points(m_unused=None):
+def grid_points():
     """(cJ, cU, cmu) of the C3 grid in the reference's loop order (src/analysis.cpp:303-308, -f J mode)."""
     p1 = 1.0 + np.arange(GRID) * 1.0  # U coefficient sweeps [J, J + r]  (SURVEY.md D9)
     p2 = 0.0 + np.arange(GRID) * 1.0  # mu
@@ -104,21 +118,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_sample(maxit, threads, full_matvecs):
-    """Bounded CPU sample of one C3 point (J=1, U=4, mu=1) on `threads` cores with oracle/_ref; returns the dict
-    for cpu_baseline.  full_matvecs = H.v count of the converged solve (from the GPU solver, same algorithm)."""
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU side: the compiled reference (oracle/_ref), never the product path
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_converged_matvecs():
+    """H.v count of the reference's own converged solve of the sample point (J=1, U=4, mu=1) at m = n = 12, as recorded when
+    the golden fixture was generated from oracle/_ref (tests/golden/reference_golden_meta.json)."""
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_golden_meta.json")))
+    return int(meta["point_12_12_1_4_1"]["nmatvec"])
+
+
+def reference_sample(maxit, threads):
+    """Bounded CPU sample: `threads` concurrent copies (one per core) of the reference solver call on the C3 point
+    (J=1, U=4, mu=1), stopped after `maxit` restarts; scaled to the H.v count of the reference's own converged solve."""
     import ref_lib as R
     if not R.available():
         return None
+    full = reference_converged_matvecs()
     info = R.partial(12, 12, 1, 4, 1, maxit, threads)
-    per_point = info["seconds"] * (full_matvecs / max(info["nmatvec"], 1))
+    per_point = info["seconds"] * (full / max(info["nmatvec"], 1))
     return {
         "value": info["threads"] / per_point, "unit": "points/s", "cores": info["threads"], "kind": "reference",
-        "sample": (f"{info['threads']} concurrent copies (one per core) of the C3 point (J=1,U=4,mu=1) through the patched "
-                   f"reference solver call (Spectra GenEigsSolver nev=20 ncv=41), stopped after {info['nrestart']} restart(s) = "
-                   f"{info['nmatvec']} H.v in {info['seconds']:.1f} s; scaled to the {full_matvecs} H.v of the converged solve"),
+        "sample": (f"{info['threads']} concurrent copies (one per core) of the C3 point (J=1,U=4,mu=1) through the compiled reference's "
+                   f"solver call (Spectra GenEigsSolver nev=20 ncv=41), stopped after {info['nrestart']} restart(s) = {info['nmatvec']} H.v in "
+                   f"{info['seconds']:.1f} s; scaled to the {full} H.v the same reference binary needed to converge this point "
+                   f"(tests/golden/reference_golden_meta.json); U=4 is one of the cheapest points of the grid (U=32 needs 3377 H.v)"),
         "seconds": info["seconds"], "sample_matvecs": info["nmatvec"], "setup_seconds": info["setup_seconds"],
     }
+
+
+def reference_converged(threads):
+    """`threads` grid points of C3 (U = 1..threads, mu = 0; one per core) through the reference's per-point loop body
+    (src/analysis.cpp:302-343 via oracle/_ref/ref_harness points) to CONVERGENCE: a measured points/s, no extrapolation."""
+    import ref_lib as R
+    npts = max(1, min(threads, 16))
+    r, info = R.points(12, 12, "J", 1.0, 1.0, 0.0, 1.0, npts, 1, threads=npts, want=True, timeout=3 * 3600)
+    return {"points": npts, "seconds": info["seconds"], "setup_seconds": info["setup_seconds"], "threads": info["threads"],
+            "value": npts / info["seconds"], "U": [1.0 + i for i in range(npts)],
+            "out3_first": [float(v) for v in r["out5"][0][2:]], "out3_all": r["out5"][:, 2:].tolist()}
 
 
 def run_reference(args):
@@ -126,30 +163,47 @@ def run_reference(args):
     if rank != 0:
         return 0
     import ref_lib as R
-    cfg = {"workload": "C3: closed chain m=12 n=12 (D=1352078), 32x32 grid of -J 1 -U 0 -u 0 -r 31 -s 1 -f J",
-           "points_per_step": os.cpu_count()}
     if not R.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference at build time)"}))
         return 0
-    full = args.full_matvecs
+    cores = os.cpu_count()
     vals = []
     for s in range(args.warmup + args.steps):
-        r = reference_sample(args.ref_maxit, os.cpu_count(), full)
+        r = reference_sample(args.ref_maxit, cores)
         if s >= args.warmup:
             vals.append(r)
-    v = float(np.mean([x["value"] for x in vals]))
+    v_est = float(np.mean([x["value"] for x in vals]))
     ms = float(np.mean([x["seconds"] for x in vals])) * 1e3
+    conv = None
+    if not args.no_ref_converged:
+        try:
+            conv = reference_converged(cores)
+        except Exception as ex:
+            conv = {"error": str(ex)}
+    measured = conv is not None and "value" in conv
+    v = conv["value"] if measured else v_est
+    if measured:
+        sample = (f"{conv['points']} grid points of C3 (J=1, U=1..{conv['points']}, mu=0), one per core, through the compiled reference's "
+                  f"per-point loop body (eigensolve nev=20 ncv=41 tol=1e-10 + all observables) to CONVERGENCE: {conv['seconds']:.0f} s wall "
+                  f"(measured, no extrapolation; the cheaper half of the grid's U range, so the full-grid rate is lower). "
+                  f"Each of the {args.steps} timed steps is a bounded sample ({vals[-1]['sample_matvecs']} H.v per copy, {ms / 1e3:.1f} s) whose "
+                  f"extrapolated rate is {v_est:.4f} points/s at U=4")
+    else:
+        sample = vals[-1]["sample"]
     line = {
         "impl": "reference", "metric": "phase_diagram_points_per_sec", "value": v, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {k: vals[-1][k] for k in ("unit", "cores", "kind", "sample")} | {"value": v},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": CONFIG,
+        "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "bounded_step_estimate": {"value": v_est, "unit": "points/s", "note": vals[-1]["sample"]},
+        "converged_batch": conv,
     }
     print(json.dumps(line))
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,10 +217,11 @@ def main():
                     help="H.v kernel of the eigensolver: matrix-free (chain-specialised, faster at m=n=12) or stored SELL-32")
     ap.add_argument("--hv-reps", type=int, default=50)
     ap.add_argument("--ref-maxit", type=int, default=1)
-    ap.add_argument("--full-matvecs", type=int, default=REF_MEAN_MATVECS,
-                    help="H.v count of a converged C3 solve used to scale the bounded CPU sample")
+    ap.add_argument("--no-ref-converged", action="store_true", help="--impl reference: skip the fully converged batch (12+ min)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-c5", action="store_true", help="skip the m=n=14 matrix-free H.v timing")
+    ap.add_argument("--no-c5", action="store_true", help="skip the m=n=14 measurements")
+    ap.add_argument("--no-small", action="store_true", help="skip the C1 / C2 sweeps")
+    ap.add_argument("--no-stored", action="store_true", help="skip the stored-kernel step")
     ap.add_argument("--m", type=int, default=12)
     ap.add_argument("--n", type=int, default=12)
     args = ap.parse_args()
@@ -192,6 +247,7 @@ def main():
     K, W = args.steps, args.warmup
     m, n = args.m, args.n
     kernel = capi.HV_STORED if args.kernel == "stored" else capi.HV_MATRIX_FREE
+    peak, peak_src = peaks()
 
     cJ, cU, cmu = grid_points()
     uperm = np.random.default_rng(0).permutation(GRID)
@@ -233,10 +289,11 @@ def main():
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    matvecs = []
+    matvecs, timed_out3 = [], []
     for s in range(W, W + K):
         out3, infos = ctx.points(*step_points(s), kernel=kernel)
         matvecs += [i["nmatvec"] for i in infos]
+        timed_out3.append(out3.copy())
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -257,8 +314,10 @@ def main():
     ctx2 = pkg.Context(local)
     ctx2.setup(m, n)
     ctx2.set_batch(args.batch)
+    e2e_out3 = []
     for s in range(W, W + K):
-        ctx2.points(*step_points(s), kernel=kernel)
+        o3, _ = ctx2.points(*step_points(s), kernel=kernel)
+        e2e_out3.append(o3.copy())
     torch.cuda.synchronize()
     wall = time.perf_counter() - w0
     h2d, d2h = ctx2.transfer_bytes()
@@ -268,13 +327,72 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall = float(t.item())
     e2e = {"value": (N * P * K) / wall, "unit": "points/s", "h2d_bytes_per_step": int(h2d / K),
-           "d2h_bytes_per_step": int(d2h / K), "includes": "bh_setup (basis + CSR build) + bh_points, host buffers"}
+           "d2h_bytes_per_step": int(d2h / K), "includes": "bh_setup (basis build) + bh_points, host buffers"}
 
-    # ---- roofline: the stored-CSR H.v kernel alone (rank 0's GPU; every rank runs it to stay in step) ----
+    # ---- validation of what was timed: both arms bit-identical, scale invariance (KA8), one golden point of the reference ----
+    checks = {}
+    a3, b3 = np.concatenate(timed_out3), np.concatenate(e2e_out3)
+    checks["value_arm_equals_e2e_arm"] = bool(np.array_equal(a3, b3))
+    if not checks["value_arm_equals_e2e_arm"]:
+        raise SystemExit(f"bench.py: the timed region and the e2e arm disagree: max diff {np.abs(a3 - b3).max()}")
+    if (m, n) == (12, 12):
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
+        want = gold["point_12_12_1_4_1_out5"][2:]
+        got = ctx.point(1.0, 4.0, 1.0, kernel=kernel)
+        checks["golden_point_12_12_1_4_1"] = bool(np.allclose(got["out3"], want, rtol=1e-9, atol=1e-12))
+        scaled = ctx.point(2.0, 8.0, 2.0, kernel=kernel)  # KA8: (J, U, mu) -> lambda (J, U, mu) leaves the three columns unchanged
+        checks["scale_invariance_KA8"] = bool(np.allclose(scaled["out3"], got["out3"], rtol=1e-8, atol=1e-11))
+        if not (checks["golden_point_12_12_1_4_1"] and checks["scale_invariance_KA8"]):
+            raise SystemExit(f"bench.py: parity check failed: {checks} got {got['out3']} want {want} scaled {scaled['out3']}")
+
+    # ---- per-kernel timing of the same step: CUDA event pairs around every launch, on the launching stream ----
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record(stream)
+    nprof = min(K, 2)
+    for s in range(W, W + nprof):
+        ctx.points(*step_points(s), kernel=kernel)
+    pe1.record(stream)
+    torch.cuda.synchronize()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    prof_ms = pe0.elapsed_time(pe1)
+    traffic = {}
+    tf = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf))
+        except Exception:
+            traffic = {}
+
+    def entry(name, rec, note=None):
+        ms = rec["ms"] / max(rec["launches"], 1)
+        ab = rec["bytes"] / max(rec["launches"], 1)
+        gbs = ab / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        e = {"kernel": KERNEL_NAMES.get(name, name), "class": name, "bound": "hbm", "launches": rec["launches"],
+             "ms_per_launch": ms, "algorithmic_bytes_per_launch": ab, "achieved": gbs, "peak": peak, "unit": "GB/s",
+             "frac": gbs / peak, "share_of_step": rec["ms"] / prof_ms if prof_ms > 0 else None,
+             "traffic": traffic.get(name)}
+        if note:
+            e["note"] = note
+        return e
+
+    notes = {
+        "step": "bytes = 8 D (k + 3): w and the k basis columns read once, f and v_{k} written (k = columns orthogonalised against, 21..41)",
+        "hv_batch4": "bytes = 4 x 16 D (SURVEY.md 8d matrix-free figure per vector); L1/issue-bound at m=n=12: x is L2-resident",
+        "hv_batch2": "bytes = 2 x 16 D", "hv_free": "bytes = 16 D", "restart": "bytes = 8 D (ncv + k_kept)",
+        "gram": "bytes = 16 D ncv", "spdm": "bytes = 16 D m",
+    }
+    path = [entry(k, v, notes.get(k)) for k, v in prof.items() if v["launches"] > 0]
+    path.sort(key=lambda e: -(e["share_of_step"] or 0))
+
+    # ---- the stored H.v kernel (K3): alone warm, alone cold (a 512 MB write between launches), and inside a solve ----
     D = ctx.D
     x = torch.empty(D, dtype=torch.float64, device="cuda")
     y = torch.empty(D, dtype=torch.float64, device="cuda")
     ctx.lcg_fill_dev(x.data_ptr(), D)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float64, device="cuda")  # 512 MB > 126 MB of L2
     hv = {}
     for name, kid in (("stored", capi.HV_STORED), ("matrix_free", capi.HV_MATRIX_FREE)):
         for _ in range(5):
@@ -289,94 +407,210 @@ def main():
         ms = a.elapsed_time(b) / args.hv_reps
         ab = ctx.hv_algorithmic_bytes(kid)
         hv[name] = {"ms": ms, "algorithmic_bytes": ab, "gbs": ab / (ms * 1e-3) / 1e9}
-    # MatOp seam with host vectors (H2D + kernel + D2H), the call Spectra would make
-    xh = np.random.default_rng(1).uniform(-0.5, 0.5, D)
-    ctx.hv(1.0, 4.0, 1.0, xh, kernel=capi.HV_STORED, order=capi.LEX)
-    t0 = time.perf_counter()
-    for _ in range(5):
-        ctx.hv(1.0, 4.0, 1.0, xh, kernel=capi.HV_STORED, order=capi.LEX)
-    hv_host_ms = (time.perf_counter() - t0) / 5 * 1e3
-
-    # config 5 shape for the record (N = 1 only): matrix-free H.v at m = n = 14, algorithmic bytes 16 D
-    c5 = None
-    if world == 1 and not args.no_c5:
-        try:
-            c14 = pkg.Context(local)
-            c14.set_stream(stream.cuda_stream)
-            c14.setup(14, 14)
-            D14 = c14.D
-            x14 = torch.empty(D14, dtype=torch.float64, device="cuda")
-            y14 = torch.empty(D14, dtype=torch.float64, device="cuda")
-            c14.lcg_fill_dev(x14.data_ptr(), D14)
-            for _ in range(3):
-                c14.hv_dev(1.0, 4.0, 1.0, x14.data_ptr(), y14.data_ptr(), capi.HV_MATRIX_FREE)
-            torch.cuda.synchronize()
+        cold = 0.0
+        nc = 10
+        for _ in range(nc):
+            flush.fill_(1.0)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            for _ in range(10):
-                c14.hv_dev(1.0, 4.0, 1.0, x14.data_ptr(), y14.data_ptr(), capi.HV_MATRIX_FREE)
+            ctx.hv_dev(1.0, 4.0, 1.0, x.data_ptr(), y.data_ptr(), kid)
             b.record(stream)
             torch.cuda.synchronize()
-            ms14 = a.elapsed_time(b) / 10
-            ab14 = c14.hv_algorithmic_bytes(capi.HV_MATRIX_FREE)
-            c5 = {"workload": "C5 shape: closed chain m=14 n=14 (D=20058300), matrix-free H.v", "ms": ms14,
-                  "algorithmic_bytes": ab14, "gbs": ab14 / (ms14 * 1e-3) / 1e9}
-            c14.close()
-            del x14, y14
-        except Exception as ex:
+            cold += a.elapsed_time(b)
+        hv[name]["cold_ms"] = cold / nc
+        hv[name]["cold_gbs"] = ab / (cold / nc * 1e-3) / 1e9
+    del flush
+    path.append({"kernel": KERNEL_NAMES["hv_stored"] + " alone, back to back (warm L2)", "class": "hv_stored_alone_warm", "bound": "hbm",
+                 "launches": args.hv_reps, "ms_per_launch": hv["stored"]["ms"], "algorithmic_bytes_per_launch": hv["stored"]["algorithmic_bytes"],
+                 "achieved": hv["stored"]["gbs"], "peak": peak, "unit": "GB/s", "frac": hv["stored"]["gbs"] / peak,
+                 "share_of_step": 0.0, "traffic": traffic.get("hv_stored"),
+                 "note": "not on the timed path (the sweep runs the matrix-free kernel); bytes = 12 nnz(H) + 4 (D + 1) + 16 D"})
+    path.append({"kernel": KERNEL_NAMES["hv_stored"] + " alone, L2 flushed before every launch", "class": "hv_stored_alone_cold", "bound": "hbm",
+                 "launches": 10, "ms_per_launch": hv["stored"]["cold_ms"], "algorithmic_bytes_per_launch": hv["stored"]["algorithmic_bytes"],
+                 "achieved": hv["stored"]["cold_gbs"], "peak": peak, "unit": "GB/s", "frac": hv["stored"]["cold_gbs"] / peak,
+                 "share_of_step": 0.0, "traffic": traffic.get("hv_stored")})
+
+    # ---- the same step with the stored kernel (C3 as BASELINE.json words it), with its in-solve H.v timing ----
+    stored = None
+    if not args.no_stored and kernel != capi.HV_STORED:
+        ctx.points(*step_points(0), kernel=capi.HV_STORED)  # builds the SELL copy, warms up
+        sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        sa.record(stream)
+        so3, _ = ctx.points(*step_points(W), kernel=capi.HV_STORED)
+        sb.record(stream)
+        torch.cuda.synchronize()
+        sms = sa.elapsed_time(sb)
+        ctx.profile_enable(True)
+        ctx.profile_read()
+        pj, pu, pm = step_points(W)
+        ctx.points(pj[:2], pu[:2], pm[:2], kernel=capi.HV_STORED)
+        sp = ctx.profile_read()
+        ctx.profile_enable(False)
+        stored = {"value": P / (sms * 1e-3), "unit": "points/s", "points": P, "lockstep": "not available for the stored kernel: one point at a time",
+                  "equals_matrix_free_step": bool(np.allclose(so3, timed_out3[0], rtol=1e-9, atol=1e-12))}
+        if sp["hv_stored"]["launches"]:
+            ent = entry("hv_stored", sp["hv_stored"], "inside a solve: every launch follows a sweep over the 454 MB Krylov basis (cold L2)")
+            ent["class"] = "hv_stored_in_solve"
+            ent["share_of_step"] = None
+            path.append(ent)
+            stored["hv_in_solve_ms"] = ent["ms_per_launch"]
+
+    # ---- config 5 ----
+    c5 = None
+    if not args.no_c5:
+        try:
+            c5 = bench_c5(pkg, capi, torch, dist, stream, local, rank, world, peak)
+        except Exception as ex:  # never lose the C3 line to the C5 side measurement
             c5 = {"error": str(ex)}
 
-    peak, peak_src = peaks()
-    if c5 and "gbs" in c5:
-        c5["frac_of_hbm_peak"] = c5["gbs"] / peak
-    traffic = None
-    tf = os.path.join(ROOT, "profiles", "hv_traffic.json")
-    if os.path.exists(tf):
-        try:
-            traffic = json.load(open(tf)).get("k_hv_sell_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_hv_sell (stored H.v, K3, SELL-32 layout)", "achieved": hv["stored"]["gbs"], "peak": peak,
-                "unit": "GB/s", "frac": hv["stored"]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": hv["stored"]["algorithmic_bytes"], "ms_per_launch": hv["stored"]["ms"]}
+    # ---- configs 1 and 2: the full 11 x 11 grids through the same call ----
+    small = None
+    if world == 1 and not args.no_small:
+        small = {}
+        p1 = 1.0 + np.arange(11.0)
+        p2 = np.arange(11.0)
+        sU, smu = [a.reshape(-1) for a in np.meshgrid(p1, p2, indexing="ij")]
+        for name, mm in (("C1", 8), ("C2", 10)):
+            try:
+                c = pkg.Context(local)
+                c.set_stream(stream.cuda_stream)
+                c.setup(mm, mm)
+                c.set_batch(args.batch)
+                c.points(np.ones(8), sU[:8], smu[:8], kernel=capi.HV_MATRIX_FREE)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                o3, _ = c.points(np.ones(len(sU)), sU, smu, kernel=capi.HV_MATRIX_FREE)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                small[name] = {"workload": f"closed chain m=n={mm}, 11x11 grid of -J 1 -U 0 -u 0 -r 10 -s 1 -f J", "points": len(sU),
+                               "seconds": dt, "value": len(sU) / dt, "unit": "points/s"}
+                if mm == 8:
+                    # the committed output of the compiled reference CLI for exactly this sweep
+                    rows = [l.split() for l in open(os.path.join(ROOT, "tests", "golden", "phase_m8_C1.txt")).read().splitlines()[1:]]
+                    ref = np.array([[float(v) for v in r] for r in rows])
+                    small[name]["matches_reference_phase_txt"] = bool(
+                        np.array_equal(ref[:, 0], sU) and np.array_equal(ref[:, 1], smu) and np.allclose(o3, ref[:, 2:], rtol=2e-6, atol=1e-9))
+                c.close()
+            except Exception as ex:
+                small[name] = {"error": str(ex)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    full_mv = args.full_matvecs  # the reference algorithm's count, not the accelerated solver's
     cpu = None
     if N == 1 and not args.no_cpu_baseline:
         try:
-            cpu = reference_sample(args.ref_maxit, os.cpu_count(), full_mv)
+            cpu = reference_sample(args.ref_maxit, os.cpu_count())
         except Exception as ex:  # the baseline is a report, never a reason to lose the GPU line
             cpu = {"value": None, "unit": "points/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
         if cpu is None:
             cpu = {"value": None, "unit": "points/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": "oracle/_ref not built on this host"}
 
+    on_path = [e for e in path if e.get("share_of_step")]
+    top = max(on_path, key=lambda e: e["share_of_step"]) if on_path else path[0]
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved"], "peak": peak, "unit": "GB/s", "frac": top["frac"],
+                "traffic": top.get("traffic"), "peak_source": peak_src, "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"],
+                "ms_per_launch": top["ms_per_launch"], "share_of_step": top["share_of_step"], "launches": top["launches"],
+                "how": f"CUDA event pairs around every launch of the class on the launching stream, {nprof} step(s) of the timed workload"}
     line = {
         "metric": "phase_diagram_points_per_sec", "value": value, "unit": "points/s", "n_gpus": N, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "C3: closed chain m=12 n=12 (D=1352078, nnz(H)=18282446), 32x32 grid of -J 1 -U 0 -u 0 -r 31 -s 1 -f J",
-                   "m": m, "n": n, "points_per_gpu_per_step": P, "nev": 20, "ncv": 41, "tol": 1e-10, "hv_kernel": args.kernel, "lockstep_batch": args.batch,
-                   "solver": "thick-restart Lanczos on a degree-%s Chebyshev filter of H + Rayleigh-Ritz of H" % os.environ.get("BH_CHEB_DEGREE", "8"),
-                   "l2": "inputs larger than L2 (Krylov basis 454 MB per point; stored H 433 MB for the roofline kernel)",
-                   "mean_matvecs_per_point": int(np.mean(matvecs)) if matvecs else None, "setup_seconds": setup_s},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "hv": {"stored": hv["stored"], "matrix_free": hv["matrix_free"], "host_vectors_ms": hv_host_ms,
-               "note": "roofline = the stored H.v the metric names (C3); the sweep itself runs the matrix-free chain kernel "
-                       "(instruction-bound, 8x less HBM traffic), whose 16*D figure is listed here and for C5 below"},
-        "c5_matrix_free_hv": c5,
+        "data": "synthetic", "config": CONFIG,
+        "impl_config": {"points_per_gpu_per_step": P, "hv_kernel": args.kernel, "lockstep_batch": args.batch,
+                        "solver": "thick-restart Lanczos on a degree-%s Chebyshev filter of H + Rayleigh-Ritz of H" % os.environ.get("BH_CHEB_DEGREE", "8"),
+                        "mean_matvecs_per_point": int(np.mean(matvecs)) if matvecs else None, "setup_seconds": setup_s},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_path": path,
+        "checks": checks,
+        "hv": {"stored": hv["stored"], "matrix_free": hv["matrix_free"]},
+        "stored_kernel": stored, "small_configs": small,
     }
+    if c5 is not None:
+        line["c5_partitioned" if world > 1 else "c5_matrix_free_hv"] = c5
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bench_c5(pkg, capi, torch, dist, stream, local, rank, world, peak):
+    """Config 5 (closed chain m = n = 14, D = 20 058 300, matrix-free).  One GPU: H.v timing against the 16 D roofline and the
+    nev = 2 solve (ground state + gap).  Several GPUs: the row-partitioned solve, checked against the single-GPU solve."""
+    m = n = 14
+    pars = (1.0, 4.0, 1.0)
+    if world == 1:
+        c14 = pkg.Context(local)
+        c14.set_stream(stream.cuda_stream)
+        c14.setup(m, n)
+        D14 = c14.D
+        x14 = torch.empty(D14, dtype=torch.float64, device="cuda")
+        y14 = torch.empty(D14, dtype=torch.float64, device="cuda")
+        c14.lcg_fill_dev(x14.data_ptr(), D14)
+        for _ in range(3):
+            c14.hv_dev(*pars, x14.data_ptr(), y14.data_ptr(), capi.HV_MATRIX_FREE)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(10):
+            c14.hv_dev(*pars, x14.data_ptr(), y14.data_ptr(), capi.HV_MATRIX_FREE)
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms14 = a.elapsed_time(b) / 10
+        ab14 = c14.hv_algorithmic_bytes(capi.HV_MATRIX_FREE)
+        out = {"workload": "C5 shape: closed chain m=14 n=14 (D=20058300), matrix-free H.v", "ms": ms14,
+               "algorithmic_bytes": ab14, "gbs": ab14 / (ms14 * 1e-3) / 1e9}
+        out["frac_of_hbm_peak"] = out["gbs"] / peak
+        del x14, y14
+        c14.eigs(*pars, nev=2, ncv=12, kernel=capi.HV_MATRIX_FREE, order=capi.LEX, maxit=2, allow_noconv=True)  # warm-up (allocations)
+        r = c14.eigs(*pars, nev=2, ncv=12, kernel=capi.HV_MATRIX_FREE, order=capi.LEX)
+        out["ground_state_and_gap"] = {"solve_s": r["seconds"], "nmatvec": r["nmatvec"], "E0": float(r["evals"][0]),
+                                       "gap": float(r["evals"][1] - r["evals"][0])}
+        c14.close()
+        return out
+    # ---- row-partitioned over the ranks of this job ----
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.tensor(list(pkg.Context.dist_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx = pkg.Context(local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.dist_init(world, rank, bytes(idt.cpu().numpy().tolist()))
+    ctx.setup_partitioned(m, n)
+    ctx.eigs(*pars, nev=2, ncv=12, kernel=capi.HV_MATRIX_FREE, order=capi.LEX, maxit=2, allow_noconv=True)  # warm-up
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.perf_counter()
+    r = ctx.eigs(*pars, nev=2, ncv=12, kernel=capi.HV_MATRIX_FREE, order=capi.LEX)
+    torch.cuda.synchronize()
+    dist.barrier()
+    solve_s = time.perf_counter() - t1
+    t = torch.tensor([solve_s], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {"workload": "C5: closed chain m=14 n=14 (D=20058300), nev=2 ncv=12 (ground state + gap), rows partitioned over the ranks",
+           "world": world, "solve_s": float(t.item()), "nmatvec": r["nmatvec"], "E0": float(r["evals"][0]),
+           "gap": float(r["evals"][1] - r["evals"][0])}
+    ctx.dist_finalize()
+    ctx.close()
+    if rank == 0:
+        one = pkg.Context(local)
+        one.set_stream(stream.cuda_stream)
+        one.setup(m, n)
+        one.eigs(*pars, nev=2, ncv=12, kernel=capi.HV_MATRIX_FREE, order=capi.LEX, maxit=2, allow_noconv=True)
+        s = one.eigs(*pars, nev=2, ncv=12, kernel=capi.HV_MATRIX_FREE, order=capi.LEX)
+        scale = np.maximum(np.abs(s["evals"]), abs(s["evals"][0]))
+        ok = bool(np.all(np.abs(s["evals"] - r["evals"]) <= 1e-10 * scale))
+        out["single_gpu_solve_s"] = s["seconds"]
+        out["single_gpu_nmatvec"] = s["nmatvec"]
+        out["max_abs_diff"] = float(np.abs(s["evals"] - r["evals"]).max())
+        out["check"] = "ok" if ok else "MISMATCH"
+        one.close()
+    dist.barrier()
+    return out
 
 
 if __name__ == "__main__":

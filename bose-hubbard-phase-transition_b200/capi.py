@@ -16,6 +16,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOCONV, ERR_UNSUPPORTED = 0, -1, -2, -3, -
 LEX, TAG_SORTED, REF_SCATTER = 0, 1, 2
 TERM_J, TERM_U, TERM_MU = 0, 1, 2
 HV_STORED, HV_MATRIX_FREE, HV_USER, HV_HYBRID = 0, 1, 2, 3
+PROF_CLASSES = ["hv_free", "hv_batch2", "hv_batch4", "hv_stored", "step", "restart", "gram", "spdm", "small"]
 
 # every symbol include/bh_b200.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [
@@ -24,6 +25,7 @@ SYMBOLS = [
     "bh_term_nnz", "bh_term_csc", "bh_hamiltonian_nnz", "bh_hamiltonian_csc", "bh_hv", "bh_hv_dev", "bh_eigs",
     "bh_spdm", "bh_gap_ratios", "bh_condensate_fraction", "bh_coherence", "bh_point", "bh_points",
     "bh_lcg_fill_dev", "bh_hv_algorithmic_bytes", "bh_load_matrix", "bh_ctx_set_batch",
+    "bh_ctx_profile_enable", "bh_ctx_profile_read",
     "bh_dist_unique_id", "bh_dist_init", "bh_dist_finalize", "bh_setup_partitioned", "bh_partition",
 ]
 
@@ -83,6 +85,8 @@ def load():
     L.bh_point.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, C.POINTER(EigsInfo)]
     L.bh_points.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
     L.bh_ctx_set_batch.argtypes = [vp, C.c_int]
+    L.bh_ctx_profile_enable.argtypes = [vp, C.c_int]
+    L.bh_ctx_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), dp, dp]
     L.bh_dist_unique_id.argtypes = [vp]
     L.bh_dist_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.bh_dist_finalize.argtypes = [vp]
@@ -183,6 +187,19 @@ class Context:
         """bh_points solves `batch` (1..4) grid points in lockstep, sharing their H.v launches."""
         self._check(self.L.bh_ctx_set_batch(self.h, int(batch)))
         return self
+
+    def profile_enable(self, on=True):
+        """Bracket every launch of the main kernel classes with CUDA events on the launching stream (bench.py's roofline)."""
+        self._check(self.L.bh_ctx_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """-> {class: dict(launches, ms, bytes)} since the last read."""
+        out = {}
+        for cls, name in enumerate(PROF_CLASSES):
+            n, ms, by = C.c_int64(0), C.c_double(0), C.c_double(0)
+            self._check(self.L.bh_ctx_profile_read(self.h, cls, C.byref(n), C.byref(ms), C.byref(by)))
+            out[name] = dict(launches=n.value, ms=ms.value, bytes=by.value)
+        return out
 
     def launch_count(self):
         return self.L.bh_ctx_launch_count(self.h)

@@ -225,7 +225,10 @@ static int apply_filters(bh_ctx* parent, bh_batch_hub* hub, const int* fib, int 
         if (!last) a.yi = hub->d_il[k % 3];
         batch_fn fn = batch_kernel(m, nb, k >= 2);
         if (!fn) return bh_fail(parent, BH_ERR_UNSUPPORTED, "batched H.v: unsupported chain length");
-        fn<<<grid, 256, 0, parent->stream>>>(parent->d_tab, D, parent->d_states, parent->d_dU, a);
+        {
+            BhProfScope prof(parent, nb == 4 ? BH_PROF_HV_BATCH4 : BH_PROF_HV_BATCH2, 16.0 * (double)D * nb);
+            fn<<<grid, 256, 0, parent->stream>>>(parent->d_tab, D, parent->d_states, parent->d_dU, a);
+        }
         BH_LAUNCHED(parent);
     }
     BH_CUDA(parent, cudaGetLastError());
@@ -333,6 +336,9 @@ static int ensure_children(bh_ctx* ctx, int nb)
         c->own_stream = false;
         c->fiber = (int)ctx->children.size();
         c->launches = c->h2d_bytes = c->d2h_bytes = 0;
+        c->prof_on = false;  // event records live on the parent (BhProfScope)
+        c->prof.clear();
+        c->prof_free.clear();
         c->d_V = c->d_w = c->d_f = c->d_scal = c->d_part = c->d_small = c->d_spdm_scratch = c->d_x = c->d_y = nullptr;
         c->d_counter = nullptr;
         c->h_pinned = nullptr;

@@ -34,8 +34,20 @@ struct BhTables {
     double logp[BH_MAX_SITES];  // log(prime_i), host glibc values (src/hamiltonian.cpp:94,144)
 };
 
+struct BhProfRec {
+    cudaEvent_t a, b;
+    int cls;
+    double bytes;
+};
+
 struct bh_ctx {
     int device = 0;
+    // per-kernel event timing (bh_ctx_profile_*): records live on the root context (lockstep children share it)
+    bool prof_on = false;
+    std::vector<BhProfRec> prof;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[BH_PROF_NCLASSES] = {0}, prof_bytes[BH_PROF_NCLASSES] = {0};
+    int64_t prof_n[BH_PROF_NCLASSES] = {0};
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -173,6 +185,18 @@ int bh_fail(bh_ctx* ctx, int code, const std::string& msg);
         (ctx)->d2h_bytes += (int64_t)(bytes);                                                             \
         BH_CUDA((ctx), cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (ctx)->stream));    \
     } while (0)
+
+// ---- per-kernel event timing: BhProfScope brackets the launches issued while it is alive ----
+void bh_prof_begin(bh_ctx* ctx, int cls, double bytes);
+void bh_prof_end(bh_ctx* ctx);
+struct BhProfScope {
+    bh_ctx* root;
+    BhProfScope(bh_ctx* ctx, int cls, double bytes) : root(ctx->parent ? ctx->parent : ctx)
+    {
+        if (root->prof_on) bh_prof_begin(root, cls, bytes); else root = nullptr;
+    }
+    ~BhProfScope() { if (root) bh_prof_end(root); }
+};
 
 // ---- internal entry points (defined across the .cu files) ----
 int bh_release_system(bh_ctx* ctx);

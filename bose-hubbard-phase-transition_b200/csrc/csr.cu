@@ -372,7 +372,8 @@ static int build_sell(bh_ctx* ctx)
                                                          ctx->d_sell_ptr, ctx->d_sell_col, ctx->d_sell_valJ, ctx->d_sell_diag);
     BH_LAUNCHED(ctx);
     BH_CUDA(ctx, cudaGetLastError());
-    ctx->sell_valid = false;
+    ctx->sell_valid = ctx->sell_partial_valid = false;
+    ctx->sell_cJ = ctx->sell_cU = ctx->sell_cmu = 0.0;
     return BH_OK;
 }
 

@@ -135,7 +135,8 @@ int bh_release_system(bh_ctx* ctx)
     free_dev(ctx->d_sell_valJ); ctx->d_sell_valJ = nullptr;
     free_dev(ctx->d_sell_valH); ctx->d_sell_valH = nullptr;
     free_dev(ctx->d_sell_diag); ctx->d_sell_diag = nullptr;
-    ctx->sell_valid = false;
+    ctx->sell_valid = ctx->sell_partial_valid = false;
+    ctx->sell_cJ = ctx->sell_cU = ctx->sell_cmu = 0.0;
     ctx->sell_nslices = ctx->sell_entries = 0;
     ctx->hyb_split = -1;
     free_dev(ctx->d_tags); ctx->d_tags = nullptr;
@@ -158,8 +159,75 @@ extern "C" int bh_ctx_destroy(bh_ctx* ctx)
 {
     if (!ctx) return BH_OK;
     bh_release_system(ctx);
+    if (ctx->nccl_comm) bh_dist_finalize(ctx);  // a context that joined a communicator leaves it here
+    bh_ctx_profile_enable(ctx, 0);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return BH_OK;
+}
+
+// ---- per-kernel event timing ----
+static cudaEvent_t prof_event(bh_ctx* root)
+{
+    if (!root->prof_free.empty()) {
+        cudaEvent_t e = root->prof_free.back();
+        root->prof_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void bh_prof_begin(bh_ctx* root, int cls, double bytes)
+{
+    BhProfRec r{prof_event(root), prof_event(root), cls, bytes};
+    cudaEventRecord(r.a, root->stream);
+    root->prof.push_back(r);
+}
+
+void bh_prof_end(bh_ctx* root) { cudaEventRecord(root->prof.back().b, root->stream); }
+
+static void prof_collect(bh_ctx* ctx)
+{
+    if (ctx->prof.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (const BhProfRec& r : ctx->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.cls >= 0 && r.cls < BH_PROF_NCLASSES) {
+            ctx->prof_ms[r.cls] += ms;
+            ctx->prof_bytes[r.cls] += r.bytes;
+            ctx->prof_n[r.cls]++;
+        }
+        ctx->prof_free.push_back(r.a);
+        ctx->prof_free.push_back(r.b);
+    }
+    ctx->prof.clear();
+}
+
+extern "C" int bh_ctx_profile_enable(bh_ctx* ctx, int on)
+{
+    if (!ctx) return BH_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    prof_collect(ctx);
+    ctx->prof_on = on != 0;
+    if (!on) {
+        for (cudaEvent_t e : ctx->prof_free) cudaEventDestroy(e);
+        ctx->prof_free.clear();
+    }
+    return BH_OK;
+}
+
+extern "C" int bh_ctx_profile_read(bh_ctx* ctx, int cls, int64_t* launches, double* total_ms, double* total_bytes)
+{
+    if (!ctx || cls < 0 || cls >= BH_PROF_NCLASSES) return bh_fail(ctx, BH_ERR_ARG, "bh_ctx_profile_read: bad class");
+    cudaSetDevice(ctx->device);
+    prof_collect(ctx);
+    if (launches) *launches = ctx->prof_n[cls];
+    if (total_ms) *total_ms = ctx->prof_ms[cls];
+    if (total_bytes) *total_bytes = ctx->prof_bytes[cls];
+    ctx->prof_n[cls] = 0;
+    ctx->prof_ms[cls] = ctx->prof_bytes[cls] = 0.0;
     return BH_OK;
 }
 

@@ -87,23 +87,25 @@ extern "C" int bh_dist_finalize(bh_ctx* ctx)
     return BH_OK;
 }
 
+// The collectives below are issued only by a context that is row-partitioned (bh_setup_partitioned): a context that called
+// bh_dist_init and then a plain bh_setup solves its own grid points and must not meet its peers in a collective.
 int bh_dist_allreduce_sum(bh_ctx* ctx, double* buf, int64_t count)
 {
-    if (ctx->world < 2) return BH_OK;
+    if (ctx->world < 2 || !ctx->partitioned) return BH_OK;
     BH_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));
     return BH_OK;
 }
 
 int bh_dist_allreduce_max(bh_ctx* ctx, double* buf, int64_t count)
 {
-    if (ctx->world < 2) return BH_OK;
+    if (ctx->world < 2 || !ctx->partitioned) return BH_OK;
     BH_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, ncclDouble, ncclMax, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));
     return BH_OK;
 }
 
 int bh_dist_allgather(bh_ctx* ctx, const double* send, double* recv, int64_t count_per_rank)
 {
-    if (ctx->world < 2) {
+    if (ctx->world < 2 || !ctx->partitioned) {
         BH_CUDA(ctx, cudaMemcpyAsync(recv, send, sizeof(double) * count_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
         return BH_OK;
     }

@@ -620,6 +620,10 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
     bool fused = false;
     const bool plain = (ep.s1 == 1.0 && ep.s2 == 0.0 && ep.z == nullptr);
     const int64_t D = ctx->D;
+    // algorithmic bytes of SURVEY.md section 8d (stored: 12 nnz + 4 (D + 1) + 16 D; matrix-free: 16 D per local row range)
+    const bool prof_stored = (kernel_in == BH_HV_STORED || kernel_in == BH_HV_USER);
+    BhProfScope prof(ctx, prof_stored ? BH_PROF_HV_STORED : BH_PROF_HV_FREE,
+                     prof_stored ? 12.0 * (double)ctx->nnzH + 4.0 * (double)(D + 1) + 16.0 * (double)D : 16.0 * (double)ctx->nloc);
     if (kernel == BH_HV_HYBRID) {
         // only for chains on a single GPU; everything else runs the matrix-free kernel
         if (ctx->partitioned || ctx->user_matrix || !ctx->h_tab.chain || ctx->hybrid_frac <= 0.0) {

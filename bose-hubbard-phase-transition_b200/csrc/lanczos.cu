@@ -999,10 +999,15 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
                 void* fn = coop_smem ? (void*)k_step_coop<GT_CH, COOP_NP_S, true>
                                      : (ctx->coop_ch == 4 ? (void*)k_step_coop<4, COOP_NP, false> : (void*)k_step_coop<GT_CH, COOP_NP, false>);
                 const size_t fr_bytes = coop_smem ? sizeof(double2) * COOP_NP_S * COOP_THREADS : 0;
-                BH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(coop_grid), dim3(COOP_THREADS), args, fr_bytes, st));
+                {
+                    // algorithmic bytes: w and the i + 1 basis columns read once, f and v_{i+1} written
+                    BhProfScope prof(ctx, BH_PROF_STEP, 8.0 * (double)D * (i + 1 + 3));
+                    BH_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(coop_grid), dim3(COOP_THREADS), args, fr_bytes, st));
+                }
                 BH_LAUNCHED(ctx);
                 continue;
             }
+            BhProfScope prof(ctx, BH_PROF_STEP, 8.0 * (double)D * (i + 1 + 3));
             k_local_alpha<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_w, i > 0 ? vi - ld : vi, vi, scal, i, subtract, part, counter);
             k_resid_norm<<<G, VEC_THREADS, 0, st>>>(D, ctx->d_w, vi, ctx->d_f, scal, i, part, counter);
             const int passes = first_after_restart ? 2 : 1;
@@ -1088,6 +1093,7 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
         if (knew > ncv - 1) knew = ncv - 1;
         // K6: V[:, 0..knew) <- V Y[:, 0..knew)
         BH_H2D(ctx, ctx->d_small, Y.data(), sizeof(double) * (size_t)ncv * knew);
+        BhProfScope prof(ctx, BH_PROF_RESTART, 8.0 * (double)D * (ncv + knew));
         if (tiled8)
             k_compress_tiled8<<<nblocks(D, CT8_ROWS), 256, tiled8_smem, st>>>(D, ld, V, ncv, knew, ctx->d_small);
         else if (tiled)
@@ -1253,6 +1259,7 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
             }
             if (!ctx->d_gram_part) BH_CUDA(ctx, cudaMalloc(&ctx->d_gram_part, sizeof(double) * (size_t)nparts * GRAM_N * GRAM_N));
             for (int col = 0; col < ncv; ++col) BH_TRY(plain(ctx->d_V + (int64_t)col * ld, ctx->d_hv_block + (int64_t)col * ld));
+            BhProfScope prof(ctx, BH_PROF_GRAM, 16.0 * (double)n * ncv);
             k_gram<<<nparts, 256, 0, ctx->stream>>>(n, ld, ctx->d_V, ctx->d_hv_block, ncv, ctx->d_gram_part);
             k_gram_reduce<<<(ncv * ncv + 255) / 256, 256, 0, ctx->stream>>>(nparts, ctx->d_gram_part, ncv, ctx->d_small);
             ctx->launches += 2;

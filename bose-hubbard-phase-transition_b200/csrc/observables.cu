@@ -119,8 +119,11 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
         phi_full = ctx->d_xfull;
     }
     dim3 grid(gx, m);
-    spdm_kernel(m)<<<grid, SPDM_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, phi_full, d_part);
-    k_spdm_reduce<<<1, m * m, 0, ctx->stream>>>(m, gx, d_part, 1.0 / (double)ncols, d_rho);
+    {
+        BhProfScope prof(ctx, BH_PROF_SPDM, 16.0 * (double)nloc * m);  // phi and the packed states, once per source site
+        spdm_kernel(m)<<<grid, SPDM_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, phi_full, d_part);
+        k_spdm_reduce<<<1, m * m, 0, ctx->stream>>>(m, gx, d_part, 1.0 / (double)ncols, d_rho);
+    }
     if (dist) BH_TRY(bh_dist_allreduce_sum(ctx, d_rho, m * m));
     ctx->launches += 2;
     BH_CUDA(ctx, cudaGetLastError());

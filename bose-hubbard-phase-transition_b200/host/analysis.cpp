@@ -99,10 +99,29 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
     const std::string partial_path = opt.output + ".partial";
     std::vector<char> have(total, 0);
     std::ofstream partial;
-    if (opt.resume) {
+    // the header ties the checkpoint to the sweep AND to the current nb_eigen: rows written before a variance restart
+    // (nb_eigen += 5, the whole grid repeated) must never be mixed with rows of the new round
+    auto partial_header = [&](int nbe) {
         std::ostringstream hdr;
         hdr << "# m " << m << " n " << n << " fixed " << g.fixed << " " << std::setprecision(17) << g.fixed_value << " grid " << g.p1_min << " "
-            << g.p2_min << " " << g.step1 << " " << g.num1 << " " << g.num2 << " nb_eigen " << nb_eigen;
+            << g.p2_min << " " << g.step1 << " " << g.num1 << " " << g.num2 << " nb_eigen " << nbe;
+        return hdr.str();
+    };
+    if (opt.resume) {
+        // a run killed after a variance restart left a header with a larger nb_eigen: resume in that round
+        {
+            std::ifstream probe(partial_path);
+            std::string first;
+            if (std::getline(probe, first)) {
+                for (int nbe = nb_eigen + 5; nbe <= nb_eigen + 100; nbe += 5)
+                    if (first == partial_header(nbe)) {
+                        nb_eigen = nbe;
+                        break;
+                    }
+            }
+        }
+        std::ostringstream hdr;
+        hdr << partial_header(nb_eigen);
         std::ifstream in(partial_path);
         std::string line;
         bool ok = static_cast<bool>(std::getline(in, line)) && line == hdr.str();
@@ -202,6 +221,11 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
         if (variance > variance_threshold_percent * mean) break;
         nb_eigen += 5;
         std::fill(have.begin(), have.end(), 0);  // the whole grid is repeated with more eigenvalues
+        if (opt.resume) {  // new round, new checkpoint: the rows of the previous nb_eigen are dropped
+            partial.close();
+            partial.open(partial_path, std::ios::trunc);
+            partial << partial_header(nb_eigen) << std::endl << std::setprecision(17);
+        }
     }
     for (bh_ctx* c : ctxs) bh_ctx_destroy(c);
     if (failure) std::rethrow_exception(failure);

@@ -167,7 +167,25 @@ Eigen::SparseMatrix<double> BH::max_bosons_hamiltonian(const std::vector<std::ve
     if (n_max < n_min) n_max = n_min;
     std::vector<Eigen::SparseMatrix<double>> blocks;
     int64_t total = 0;
-    for (int bosons = std::max(n_min, 1); bosons <= n_max; ++bosons) {
+    const double eps = std::numeric_limits<double>::epsilon();
+    for (int bosons = n_min; bosons <= n_max; ++bosons) {
+        if (bosons == 0) {
+            // the empty sector (src/hamiltonian.cpp:268-274 starts at n_min = 0): one state, no hop; the U / mu branches of
+            // fixed_bosons_hamiltonian (:248-253) store the explicit diagonal entry U * 0 or -mu * 0.  Built on the host
+            // (the device basis starts at one boson).
+            Eigen::SparseMatrix<double> h0(1, 1);
+            if (std::abs(J) > eps) {
+            } else if (std::abs(U) > eps) {
+                std::vector<Eigen::Triplet<double>> t{Eigen::Triplet<double>(0, 0, U * 0.0)};
+                h0.setFromTriplets(t.begin(), t.end());
+            } else if (std::abs(mu) > eps) {
+                std::vector<Eigen::Triplet<double>> t{Eigen::Triplet<double>(0, 0, -mu * 0.0)};
+                h0.setFromTriplets(t.begin(), t.end());
+            }
+            blocks.push_back(h0);
+            total += 1;
+            continue;
+        }
         auto tb = fixed_set_basis(m, bosons);
         blocks.push_back(fixed_bosons_hamiltonian(neighbours, tb.second, tb.first, m, bosons, J, U, mu));
         total += blocks.back().rows();

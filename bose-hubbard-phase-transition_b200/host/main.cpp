@@ -26,7 +26,7 @@ static void print_usage()
               << "  -r, --range     Range for varying parameters (if range is the same for each)\n"
               << "  -s, --step      Step for varying parameters (with s < r)\n"
               << "  -f --fixed      Fixed parameter (J, U or u) \n"
-              << "  -t, --type      Type of calculation (exact or mean)\n"
+              << "  -t, --type      Type of calculation (exact or mean; 'mean' is NOT part of the accelerated path: exit code 2)\n"
               << "  -i, --iterations  Number of iterations over the parameters in the mean-field approximation\n"
               << "  -e, --epsilon  Threshold for convergence in the mean-field approximation\n"
               << "  -g, --gpus      GPUs to shard the sweep over (default: all visible)\n"
@@ -112,8 +112,10 @@ int main(int argc, char* argv[])
             return 1;
         }
     } else {
+        // the self-consistent mean-field mode (src/analysis.cpp:58-178) is outside the exact-diagonalisation hot path this
+        // binary accelerates (SURVEY.md section 2 "out of scope"): distinct exit code so that scripts can tell it from a failure
         Analysis::mean_field_parameters(it, eps);
-        return 1;
+        return 2;
     }
     return 0;
 }

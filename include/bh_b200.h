@@ -148,6 +148,17 @@ int bh_dist_finalize(bh_ctx* ctx);
 int bh_setup_partitioned(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int* nbr_idx);
 int bh_partition(const bh_ctx* ctx, int64_t* row0, int64_t* nrows, int64_t* slice);
 
+/* ---- per-kernel timing (bench.py's roofline entries) ---------------------------------------------------
+ * With profiling enabled every launch of the classes below is bracketed by a pair of CUDA events on the context's
+ * stream (the launching stream); bh_ctx_profile_read synchronises, adds up launches / milliseconds / algorithmic
+ * bytes per class since the last read and clears the records.  Off by default (two event records per launch). */
+enum { BH_PROF_HV_FREE = 0 /* matrix-free H.v, one vector */, BH_PROF_HV_BATCH2 = 1, BH_PROF_HV_BATCH4 = 2 /* lockstep H.v */,
+       BH_PROF_HV_STORED = 3, BH_PROF_STEP = 4 /* Lanczos step after the H.v: three-term update + re-orthogonalisation */,
+       BH_PROF_RESTART = 5 /* V <- V Y */, BH_PROF_GRAM = 6, BH_PROF_SPDM = 7, BH_PROF_SMALL = 8 /* many-point small-system steps */,
+       BH_PROF_NCLASSES = 9 };
+int bh_ctx_profile_enable(bh_ctx* ctx, int on);
+int bh_ctx_profile_read(bh_ctx* ctx, int cls, int64_t* launches, double* total_ms, double* total_bytes);
+
 /* ---- benchmark helpers (device-resident, used by bench.py) --------------------------------------- */
 /* Fill x_dev[D] with Spectra's LCG(seed 0) uniform(-0.5,0.5) sequence (Util/SimpleRandom.h:30-64), LEX order. */
 int bh_lcg_fill_dev(bh_ctx* ctx, double* x_dev, int64_t count);

@@ -5,6 +5,10 @@ vectors for this path, so these outputs of the reference i
 
     python tests/golden/make_golden.py            # everything up to m = n = 10   (~1 min)
     python tests/golden/make_golden.py --m12      # also one m = n = 12 point     (~5 min)
+    python tests/golden/make_golden.py --points "12,12,1,16,3,chain;12,5,1,4,1,rect:4:3" --part /tmp/p1.npz
+    python tests/golden/make_golden.py --merge /tmp/p1.npz /tmp/p2.npz   # fold part files into the fixtures
+(--points runs only the listed grid points (m,n,cJ,cU,cu,lattice) and writes them to a part file, so that the
+slow m = n = 12 points can run as concurrent processes; --merge folds part files into reference_golden.npz.)
 """
 import json
 import os
@@ -19,6 +23,52 @@ from checksums import checksum_basis, checksum_csc  # noqa: E402
 
 assert R.available(), "oracle/_ref is missing: make -C oracle ref"
 gold = {}
+OUT = os.path.join(HERE, "reference_golden.npz")
+MFILE = os.path.join(HERE, "reference_golden_meta.json")
+
+
+def point_key(m, n, cJ, cU, cu, lat="chain"):
+    key = f"point_{m}_{n}_{cJ:g}_{cU:g}_{cu:g}"
+    return key if lat == "chain" else key + "_" + lat.replace(":", "-")
+
+
+if "--merge" in sys.argv:
+    old = dict(np.load(OUT))
+    meta = json.load(open(MFILE))
+    for f in sys.argv[sys.argv.index("--merge") + 1:]:
+        old.update(dict(np.load(f)))
+        meta.update(json.load(open(f + ".json")))
+    np.savez_compressed(OUT, **old)
+    json.dump(meta, open(MFILE, "w"), indent=1, sort_keys=True)
+    sys.exit(0)
+
+if "--grid" in sys.argv:
+    # --grid "m,n,fixed,cfix,p1min,p2min,step,n1,n2,lattice" --part FILE: a small sweep grid through the reference's
+    # per-point body (ref_harness points), for lattices the reference CLI cannot build itself
+    part = sys.argv[sys.argv.index("--part") + 1]
+    f = sys.argv[sys.argv.index("--grid") + 1].split(",")
+    m, n, fixed, lat = int(f[0]), int(f[1]), f[2], f[9]
+    r, info = R.points(m, n, fixed, float(f[3]), float(f[4]), float(f[5]), float(f[6]), int(f[7]), int(f[8]), threads=8, lattice=lat)
+    key = f"grid_{m}_{n}_{lat.replace(':', '-')}"
+    np.savez_compressed(part, **{key + "_out5": r["out5"], key + "_evals": r["evals"]})
+    json.dump({key: info}, open(part + ".json", "w"), indent=1, sort_keys=True)
+    print(key, info, r["out5"][:3])
+    sys.exit(0)
+
+if "--points" in sys.argv:
+    part = sys.argv[sys.argv.index("--part") + 1]
+    meta = {}
+    for spec in sys.argv[sys.argv.index("--points") + 1].split(";"):
+        f = spec.split(",")
+        m, n, cJ, cU, cu, lat = int(f[0]), int(f[1]), float(f[2]), float(f[3]), float(f[4]), f[5]
+        r, info = R.eigs(m, n, cJ, cU, cu, lattice=lat)
+        key = point_key(m, n, cJ, cU, cu, lat)
+        gold[key + "_evals"], gold[key + "_rho"], gold[key + "_out5"] = r["evals"], r["rho"], r["out5"]
+        meta[key] = info
+        print(key, info, flush=True)
+    np.savez_compressed(part, **gold)
+    json.dump(meta, open(part + ".json", "w"), indent=1, sort_keys=True)
+    sys.exit(0)
 
 # --- basis / tags, both orders (small shapes; the large ones are pinned by checksums below) ---
 for (m, n) in [(3, 2), (4, 4), (5, 3)]:
@@ -52,6 +102,11 @@ gold["maxbasis_4_3_tags"], gold["maxbasis_4_3_states"] = t, b.astype(np.int8)
 for term, (J, U, mu) in {"J": (1, 0, 0), "U": (0, 1, 0), "u": (0, 0, 1)}.items():
     o, i, v = R.max_hamiltonian(4, 1, 3, J, U, mu)
     gold[f"maxham_{term}_4_1_3_outer"], gold[f"maxham_{term}_4_1_3_inner"], gold[f"maxham_{term}_4_1_3_val"] = o, i, v
+
+# ... including the empty sector (n_min = 0: a 1 x 1 block with the explicit entry U * 0 / -mu * 0, src/hamiltonian.cpp:268)
+for term, (J, U, mu) in {"J": (1, 0, 0), "U": (0, 1.5, 0), "u": (0, 0, 0.75)}.items():
+    o, i, v = R.max_hamiltonian(4, 0, 2, J, U, mu)
+    gold[f"maxham_{term}_4_0_2_outer"], gold[f"maxham_{term}_4_0_2_inner"], gold[f"maxham_{term}_4_0_2_val"] = o, i, v
 
 # --- H.v through Spectra's MatOp ---
 for (m, n) in [(6, 6), (8, 8)]:

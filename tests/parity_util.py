@@ -1,0 +1,42 @@
+"""Helpers shared by the parity tests.
+
+The first output column (mean gap ratio, src/analysis.cpp:433-454 + :318) is r_i = min(d_i, d_{i+1}) / max(d_i, d_{i+1}) over the
+level spacings d.  Where a level is (at least) three-fold degenerate -- every 4 x 3 and 3 x 3 torus point in the fixtures --
+two consecutive spacings are both rounding noise (1e-14) and their ratio is an O(1) random number: the reference's own
+printed value is then not reproducible even by a bit-faithful restatement of its algorithm (the oracle agrees with the
+compiled reference to 1e-13 on all 20 levels of such a point and still differs by 0.013 in this column).  For those points
+the tests compare the *regularised* ratio (spacings below 1e-9 of the spectrum scale count as exact zeros, 0/0 = 0 as in the
+reference's `max == 0` branch) computed from both sets of eigenvalues, and the other two columns strictly.
+"""
+import numpy as np
+
+
+def _spacings(evals):
+    e = np.sort(np.asarray(evals, dtype=np.float64))
+    return np.diff(e), max(abs(e[0]), abs(e[-1]), 1e-300)
+
+
+def gap_ratio_conditioned(evals, rel=1e-8):
+    """True when no two consecutive spacings are both below rel * scale (the printed column is then well defined)."""
+    d, s = _spacings(evals)
+    return bool(np.maximum(d[:-1], d[1:]).min() > rel * s)
+
+
+def regularised_gap_ratio(evals, rel=1e-9):
+    d, s = _spacings(evals)
+    d = np.where(d < rel * s, 0.0, d)
+    lo, hi = np.minimum(d[:-1], d[1:]), np.maximum(d[:-1], d[1:])
+    r = np.where(hi > 0, lo / np.where(hi > 0, hi, 1.0), 0.0)
+    return float(r.mean())
+
+
+def assert_out3(got3, want3, evals_ref, evals_got, rtol=1e-9, atol=1e-12):
+    """out3 = (gap ratio, condensate fraction, coherence) against the reference's, see the module docstring."""
+    got3, want3 = np.asarray(got3), np.asarray(want3)
+    assert np.allclose(got3[1:], want3[1:], rtol=rtol, atol=atol), (got3, want3)
+    if gap_ratio_conditioned(evals_ref):
+        assert np.allclose(got3[0], want3[0], rtol=rtol, atol=atol), (got3, want3)
+    else:
+        a, b = regularised_gap_ratio(evals_got), regularised_gap_ratio(evals_ref)
+        assert abs(a - b) <= 1e-6 * max(abs(b), 1e-3), (a, b)
+        assert 0.0 <= got3[0] <= 1.0

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from checksums import checksum_basis, checksum_csc
+from parity_util import assert_out3
 
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.npz"))
@@ -70,15 +71,36 @@ def test_hv_vs_spectra_matop(pkg, ctx_factory, m, n):
 POINTS = [k[len("point_"):-len("_evals")] for k in G.files if k.startswith("point_") and k.endswith("_evals")]
 
 
+def parse_point_key(key):
+    f = key.split("_")
+    lat = f[5] if len(f) > 5 else "chain"
+    return int(f[0]), int(f[1]), float(f[2]), float(f[3]), float(f[4]), lat
+
+
 @pytest.mark.parametrize("key", sorted(POINTS))
 def test_points(pkg, ctx_factory, key):
-    m, n, cJ, cU, cu = key.split("_")
-    m, n, cJ, cU, cu = int(m), int(n), float(cJ), float(cU), float(cu)
-    ctx = ctx_factory(m, n)
-    got = ctx.point(cJ, cU, cu)
-    want = G[f"point_{key}_evals"]
+    """Every golden grid point of the compiled reference (chains m = 5..12 at U = 0.5..32, periodic rectangles 3x2, 4x2,
+    3x3, 4x3 -- BASELINE.json config 4's geometry -- up to D = 31 824): 20 levels, rho, out3, both H.v kernels."""
+    m, n, cJ, cU, cu, lat = parse_point_key(key)
+    ctx = ctx_factory(m, n, nbr_of(pkg, lat, m))
+    want = np.sort(G[f"point_{key}_evals"])
     scale = np.maximum(np.abs(want), np.abs(want[0]))
-    assert np.all(np.abs(got["evals"] - np.sort(want)) <= 1e-10 * scale), got["evals"] - want
     rho = G[f"point_{key}_rho"]
-    assert np.abs(got["rho"] - rho).max() <= 1e-10 * np.abs(rho).max()
-    assert np.allclose(got["out3"], G[f"point_{key}_out5"][2:], rtol=1e-9, atol=1e-12)
+    for kernel in (pkg.capi.HV_STORED, pkg.capi.HV_MATRIX_FREE):
+        got = ctx.point(cJ, cU, cu, kernel=kernel)
+        assert np.all(np.abs(got["evals"] - want) <= 1e-10 * scale), (kernel, got["evals"] - want)
+        assert np.abs(got["rho"] - rho).max() <= 1e-10 * np.abs(rho).max(), kernel
+        assert_out3(got["out3"], G[f"point_{key}_out5"][2:], want, got["evals"])   # see parity_util: degenerate tori
+
+
+@pytest.mark.parametrize("m,n,lx,ly", [(6, 4, 3, 2), (8, 6, 4, 2), (12, 3, 4, 3)])
+def test_rect_grid_through_points(pkg, ctx_factory, m, n, lx, ly):
+    # a 3 x 3 corner of a sweep on a periodic rectangle through bh_points, vs the reference's loop body on the same neighbours
+    out5 = G[f"grid_{m}_{n}_rect-{lx}-{ly}_out5"]
+    evals = G[f"grid_{m}_{n}_rect-{lx}-{ly}_evals"]
+    ctx = ctx_factory(m, n, pkg.capi.neighbours_rect(lx, ly))
+    for kernel in (pkg.capi.HV_STORED, pkg.capi.HV_MATRIX_FREE):
+        got, _ = ctx.points(np.ones(len(out5)), out5[:, 0], out5[:, 1], kernel=kernel)
+        for i in range(len(out5)):
+            e = ctx.point(1.0, out5[i, 0], out5[i, 1], kernel=kernel)["evals"]
+            assert_out3(got[i], out5[i, 2:], evals[i], e)

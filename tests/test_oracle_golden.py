@@ -8,6 +8,7 @@ import pytest
 from checksums import checksum_basis, checksum_csc
 
 import oracle_lib as O
+from parity_util import assert_out3
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.npz"))
 
@@ -89,6 +90,26 @@ def test_point(m, n, cJ, cU, cu):
     assert np.all(np.abs(r["evals"] - want) <= 1e-10 * scale)
     assert np.abs(r["rho"] - G[key + "_rho"]).max() <= 1e-10 * np.abs(G[key + "_rho"]).max()
     assert np.allclose(r["out3"], G[key + "_out5"][2:], rtol=1e-9, atol=1e-12)
+
+
+RECT_POINTS = [(6, 4, 1, 4, 1, "rect-3-2"), (12, 3, 1, 4, 1, "rect-4-3"), (8, 6, 1, 2, 0.5, "rect-4-2"), (9, 6, 1, 3, 1, "rect-3-3"),
+               (12, 5, 1, 12, 0, "rect-4-3")]
+
+
+@pytest.mark.parametrize("m,n,cJ,cU,cu,lat", RECT_POINTS)
+def test_point_rect_lattices(m, n, cJ, cU, cu, lat):
+    # periodic rectangles (BASELINE.json config 4's geometry; 4 x 2 has doubled vertical bonds): the oracle against
+    # the compiled reference fed the same neighbour list
+    t, b = O.basis(m, n)
+    jc = O.hopping_csc(m, nbr_of(lat, m), t, b)
+    dU, dN = O.diagonals(m, b)
+    r = O.point(m, t, b, jc, dU, dN, float(cJ), float(cU), float(cu))
+    key = f"point_{m}_{n}_{cJ:g}_{cU:g}_{cu:g}_{lat}"
+    want = G[key + "_evals"]
+    scale = np.maximum(np.abs(want), np.abs(want[0]))
+    assert np.all(np.abs(r["evals"] - want) <= 1e-10 * scale)
+    assert np.abs(r["rho"] - G[key + "_rho"]).max() <= 1e-10 * np.abs(G[key + "_rho"]).max()
+    assert_out3(r["out3"], G[key + "_out5"][2:], want, r["evals"])   # 4 x 3 / 3 x 3 tori: >= 3-fold degenerate levels
 
 
 def test_known_answers():

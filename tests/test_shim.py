@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
+from parity_util import gap_ratio_conditioned
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -122,6 +123,40 @@ def test_cli_phase_txt(name, extra):
     assert same_text >= len(want.split("\n")) - 1 - len(want.split("\n")) // 100
 
 
+@pytest.mark.parametrize("extra", [(), ("--kernel", "free"), ("--kernel", "stored", "--batch", "1")], ids=["default", "free", "stored-single"])
+@pytest.mark.parametrize("m,n,lat", [(6, 4, "3x2"), (8, 6, "4x2"), (12, 3, "4x3")])
+def test_cli_lattice_flag(m, n, lat, extra):
+    """`--lattice LXxLY` (BASELINE.json config 4's geometry reachable from the CLI): 3 x 3 sweeps on
+    periodic rectangles against the compiled reference's loop body fed the same neighbour list (the reference's own
+    square_neighbours cannot build them, src/neighbours.cpp:40-71).  On the 4 x 3 torus the gap-ratio column is rounding
+    noise in the reference itself (>= 3-fold degenerate levels, tests/parity_util.py) and is only range-checked."""
+    G = np.load(os.path.join(GOLD, "reference_golden.npz"))
+    key = f"grid_{m}_{n}_rect-{lat.replace('x', '-')}"
+    want, evals = G[key + "_out5"], G[key + "_evals"]
+    args = ["-m", m, "-n", n, "-J", 1, "-U", 0, "-u", 0, "-r", 2, "-s", 1, "-f", "J", "-t", "exact", "--lattice", lat, "--no-plot"]
+    with tempfile.TemporaryDirectory() as td:
+        p = subprocess.run([CLI] + [str(a) for a in args] + list(extra), cwd=td, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, (p.stdout[-500:], p.stderr[-500:])
+        hdr, got = read_phase(open(os.path.join(td, "phase.txt")).read())
+    assert hdr == "J 1" and got.shape == want.shape
+    assert np.array_equal(got[:, :2], want[:, :2])
+    assert np.allclose(got[:, 3:], want[:, 3:], rtol=2e-6, atol=1e-9)   # 6 significant digits in the file
+    for i in range(len(want)):
+        if gap_ratio_conditioned(evals[i]):
+            assert np.isclose(got[i, 2], want[i, 2], rtol=2e-6, atol=1e-9), (i, got[i], want[i])
+        else:
+            assert 0.0 <= got[i, 2] <= 1.0
+
+
+def test_cli_lattice_errors():
+    p = subprocess.run([CLI, "-t", "exact", "-m", "12", "-n", "3", "-J", "1", "-r", "2", "-s", "1", "-f", "J", "--lattice", "5x3"],
+                       capture_output=True, text=True)
+    assert p.returncode != 0 and "lattice" in (p.stderr + p.stdout).lower()
+    p = subprocess.run([CLI, "-t", "exact", "-m", "12", "-n", "3", "-J", "1", "-r", "2", "-s", "1", "-f", "J", "--lattice", "foo"],
+                       capture_output=True, text=True)
+    assert p.returncode == 1 and "lattice must be" in p.stderr
+
+
 def test_cli_validation_messages():
     p = subprocess.run([CLI, "-t", "foo"], capture_output=True, text=True)
     assert p.returncode == 1 and "calculation type must be 'exact' or 'mean'" in p.stderr
@@ -152,6 +187,21 @@ def test_variable_n_api_against_reference():
                         [("outer", np.int32), ("inner", np.int32), ("val", np.float64)])
         for nm in ("outer", "inner", "val"):
             assert (r[nm] == G[f"maxham_{term}_4_1_3_{nm}"]).all(), (term, nm)
+
+
+def test_variable_n_api_empty_sector():
+    # n_min = 0: the reference keeps the N = 0 sector as a 1 x 1 block (src/hamiltonian.cpp:263-274), signed zeros included
+    G = np.load(os.path.join(GOLD, "reference_golden.npz"))
+    for term, (J, U, mu) in {"J": (1, 0, 0), "U": (0, 1.5, 0), "u": (0, 0, 0.75)}.items():
+        _, r = run_shim(["maxham", 4, 0, 2, J, U, mu, "chain", "@out"],
+                        [("outer", np.int32), ("inner", np.int32), ("val", np.float64)])
+        assert (r["outer"] == G[f"maxham_{term}_4_0_2_outer"]).all() and (r["inner"] == G[f"maxham_{term}_4_0_2_inner"]).all()
+        assert (bits(r["val"]) == bits(G[f"maxham_{term}_4_0_2_val"])).all(), term
+
+
+def test_cli_mean_field_mode_is_out_of_scope():
+    p = subprocess.run([CLI, "-t", "mean", "-i", "10", "-e", "1"], capture_output=True, text=True)
+    assert p.returncode == 2 and "mean-field" in p.stderr
 
 
 def test_cli_checkpoint_resume():
