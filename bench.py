@@ -490,7 +490,7 @@ def main():
                     rows = [l.split() for l in open(os.path.join(ROOT, "tests", "golden", "phase_m8_C1.txt")).read().splitlines()[1:]]
                     ref = np.array([[float(v) for v in r] for r in rows])
                     small[name]["matches_reference_phase_txt"] = bool(
-                        np.array_equal(ref[:, 0], sU) and np.array_equal(ref[:, 1], smu) and np.allclose(o3, ref[:, 2:], rtol=2e-6, atol=1e-9))
+                        np.array_equal(ref[:, 0], sU) and np.array_equal(ref[:, 1], smu) and np.allclose(o3, ref[:, 2:], rtol=6e-6, atol=1e-9))  # the file holds 6 significant digits
                 c.close()
             except Exception as ex:
                 small[name] = {"error": str(ex)}

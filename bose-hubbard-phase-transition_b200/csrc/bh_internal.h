@@ -74,6 +74,15 @@ struct bh_ctx {
     bool partitioned = false;
     int64_t row0 = 0, nloc = 0;
     double* d_xfull = nullptr;  // all-gathered vector, world * ld doubles (global index = LEX rank)
+    // overlapped halo exchange (dist.cu): only the chunks of the other slices that this rank's hops read are exchanged
+    // (ncclSend / ncclRecv on a second communicator and stream) while the own-slice hops are computed
+    struct HaloRange { int peer; int64_t off, count; };  // off = global element offset
+    std::vector<HaloRange> halo_send, halo_recv;
+    void* nccl_comm2 = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_x_ready = nullptr, ev_halo_done = nullptr;
+    bool halo_ready = false;
+    int64_t halo_recv_elems = 0;
     std::vector<int> nbr_ptr, nbr_idx;
     BhTables h_tab;
     BhTables* d_tab = nullptr;
@@ -246,6 +255,11 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
 // NCCL plumbing (dist.cu; libnccl is dlopen'ed on first use)
 int bh_dist_allreduce_sum(bh_ctx* ctx, double* buf_dev, int64_t count);
 int bh_dist_allgather(bh_ctx* ctx, const double* send_dev, double* recv_dev, int64_t count_per_rank);
+int bh_mark_halo_chunks(bh_ctx* ctx, unsigned char* flags_dev);  // hv.cu
+int bh_dist_plan_halo(bh_ctx* ctx);                              // once per bh_setup_partitioned (chains)
+int bh_dist_halo_begin(bh_ctx* ctx, const double* x_local);      // start the exchange of x into d_xfull (communication stream)
+int bh_dist_halo_end(bh_ctx* ctx);                               // the context's stream waits for it
+void bh_dist_release_halo(bh_ctx* ctx);
 
 // host-side small dense symmetric eigen-decomposition (ascending; vectors in columns of v, column-major)
 void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::vector<double>& v);

@@ -149,6 +149,7 @@ int bh_release_system(bh_ctx* ctx)
     ctx->m = ctx->n = 0;
     ctx->D = 0;
     ctx->user_matrix = false;
+    bh_dist_release_halo(ctx);
     ctx->partitioned = false;
     ctx->row0 = ctx->nloc = 0;
     free_dev(ctx->d_xfull); ctx->d_xfull = nullptr;
@@ -533,6 +534,7 @@ static int setup_impl(bh_ctx* ctx, int m, int n, const int* nbr_ptr, const int* 
         BH_CUDA(ctx, cudaMalloc(&ctx->d_xfull, sizeof(double) * per * ctx->world));
         BH_CUDA(ctx, cudaMemsetAsync(ctx->d_xfull, 0, sizeof(double) * per * ctx->world, ctx->stream));
         BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        BH_TRY(bh_dist_plan_halo(ctx));  // chains: which parts of the other slices this rank's hops read (dist.cu)
         return BH_OK;  // matrix-free only: no stored Hamiltonian
     }
     ctx->row0 = 0;

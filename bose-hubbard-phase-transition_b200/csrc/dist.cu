@@ -5,6 +5,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "bh_internal.h"
@@ -17,6 +20,11 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 } g_nccl;
 
@@ -34,6 +42,11 @@ const char* load_nccl()
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(AllReduce, "ncclAllReduce")
     SYM(AllGather, "ncclAllGather")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    g_nccl.CommSplit = reinterpret_cast<decltype(g_nccl.CommSplit)>(dlsym(h, "ncclCommSplit"));  // NCCL >= 2.18; optional
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     g_nccl.handle = h;
@@ -74,9 +87,28 @@ extern "C" int bh_dist_init(bh_ctx* ctx, int world, int rank, const void* id128)
     return BH_OK;
 }
 
+void bh_dist_release_halo(bh_ctx* ctx)
+{
+    ctx->halo_ready = false;
+    ctx->halo_send.clear();
+    ctx->halo_recv.clear();
+    ctx->halo_recv_elems = 0;
+}
+
 extern "C" int bh_dist_finalize(bh_ctx* ctx)
 {
     if (!ctx) return BH_ERR_ARG;
+    bh_dist_release_halo(ctx);
+    if (ctx->comm_stream) {
+        cudaStreamSynchronize(ctx->comm_stream);
+        if (ctx->nccl_comm2) g_nccl.CommDestroy(static_cast<ncclComm_t>(ctx->nccl_comm2));
+        ctx->nccl_comm2 = nullptr;
+        cudaStreamDestroy(ctx->comm_stream);
+        ctx->comm_stream = nullptr;
+        if (ctx->ev_x_ready) cudaEventDestroy(ctx->ev_x_ready);
+        if (ctx->ev_halo_done) cudaEventDestroy(ctx->ev_halo_done);
+        ctx->ev_x_ready = ctx->ev_halo_done = nullptr;
+    }
     if (ctx->nccl_comm) {
         cudaStreamSynchronize(ctx->stream);
         g_nccl.CommDestroy(static_cast<ncclComm_t>(ctx->nccl_comm));
@@ -110,5 +142,105 @@ int bh_dist_allgather(bh_ctx* ctx, const double* send, double* recv, int64_t cou
         return BH_OK;
     }
     BH_NCCL(ctx, g_nccl.AllGather(send, recv, (size_t)count_per_rank, ncclDouble, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));
+    return BH_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Overlapped halo exchange for the row-partitioned matrix-free H.v (chains).  The ncclAllGather of the whole vector
+// (world * ld doubles into every rank, every H.v) is what made two GPUs slower than one; a rank's hops only read
+// part of the other slices.  Once per bh_setup_partitioned every rank marks the 4096-row chunks its hops read
+// (k_mark_halo_chain), the flag arrays are all-gathered, and each rank derives the ranges it must send to / receive
+// from every peer.  Per H.v the ranges travel by grouped ncclSend / ncclRecv on a SECOND communicator and stream,
+// straight from the caller's local vector into d_xfull at their global offsets, while the context's stream computes the
+// hops whose source is local (k_hv_free_chain_part<.., 1>); the remote hops follow once the exchange has completed.
+// ---------------------------------------------------------------------------------------------------------
+#define HALO_CHUNK 4096
+
+int bh_dist_plan_halo(bh_ctx* ctx)
+{
+    bh_dist_release_halo(ctx);
+    if (!ctx->partitioned || ctx->world < 2 || !ctx->h_tab.chain || ctx->m < 3) return BH_OK;
+    if (getenv("BH_DIST_ALLGATHER")) return BH_OK;  // the north-star baseline: full ncclAllGather per H.v
+    if (!g_nccl.CommSplit) return BH_OK;             // old NCCL: keep the all-gather path
+    BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = ctx->world;
+    const int64_t per = ctx->ld;  // slice length (equal on every rank, a multiple of 32)
+    const int64_t nchunks = (per * W + HALO_CHUNK - 1) / HALO_CHUNK;
+    if (!ctx->comm_stream) {
+        ncclComm_t c2;
+        BH_NCCL(ctx, g_nccl.CommSplit(static_cast<ncclComm_t>(ctx->nccl_comm), 0, ctx->rank, &c2, nullptr));
+        ctx->nccl_comm2 = c2;
+        BH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+        BH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_x_ready, cudaEventDisableTiming));
+        BH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo_done, cudaEventDisableTiming));
+    }
+    // flags of every rank: [W][nchunks] bytes
+    unsigned char* d_flags = nullptr;
+    BH_CUDA(ctx, cudaMalloc(&d_flags, (size_t)nchunks * W));
+    BH_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)nchunks * W, ctx->stream));
+    BH_TRY(bh_mark_halo_chunks(ctx, d_flags + (size_t)ctx->rank * nchunks));
+    BH_NCCL(ctx, g_nccl.AllGather(d_flags + (size_t)ctx->rank * nchunks, d_flags, (size_t)nchunks, ncclUint8,
+                                  static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));
+    std::vector<unsigned char> flags((size_t)nchunks * W);
+    BH_D2H(ctx, flags.data(), d_flags, flags.size());
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_flags);
+    // ranges of rank `owner`'s slice that rank `reader` reads: runs of flagged chunks clipped to the owner's slice;
+    // runs separated by fewer than 8 clean chunks are merged (fewer, larger messages)
+    auto ranges = [&](int reader, int owner, std::vector<bh_ctx::HaloRange>& out, int peer) {
+        const int64_t lo = per * owner, hi = std::min<int64_t>(ctx->D, per * (owner + 1));
+        if (hi <= lo) return;
+        const unsigned char* f = flags.data() + (size_t)reader * nchunks;
+        const int64_t c0 = lo / HALO_CHUNK, c1 = (hi + HALO_CHUNK - 1) / HALO_CHUNK;
+        int64_t run0 = -1, last = -1;
+        auto flush = [&]() {
+            if (run0 < 0) return;
+            const int64_t a = std::max(lo, run0 * HALO_CHUNK), b = std::min(hi, (last + 1) * HALO_CHUNK);
+            if (b > a) out.push_back({peer, a, b - a});
+            run0 = -1;
+        };
+        for (int64_t c = c0; c < c1; ++c) {
+            if (!f[c]) continue;
+            if (run0 >= 0 && c - last > 8) flush();
+            if (run0 < 0) run0 = c;
+            last = c;
+        }
+        flush();
+    };
+    for (int p = 0; p < W; ++p) {
+        if (p == ctx->rank) continue;
+        ranges(ctx->rank, p, ctx->halo_recv, p);  // what I read from p's slice
+        ranges(p, ctx->rank, ctx->halo_send, p);  // what p reads from mine
+    }
+    ctx->halo_recv_elems = 0;
+    for (const auto& r : ctx->halo_recv) ctx->halo_recv_elems += r.count;
+    ctx->halo_ready = true;
+    if (getenv("BH_DIST_VERBOSE"))
+        fprintf(stderr, "[bh] rank %d halo plan: %zu recv ranges (%.1f MB = %.3f D), %zu send ranges\n", ctx->rank, ctx->halo_recv.size(),
+                ctx->halo_recv_elems * 8e-6, (double)ctx->halo_recv_elems / (double)ctx->D, ctx->halo_send.size());
+    return BH_OK;
+}
+
+int bh_dist_halo_begin(bh_ctx* ctx, const double* x_local)
+{
+    // the exchange may start once x is final and the previous H.v has finished reading d_xfull: both are prior work of
+    // the context's stream
+    BH_CUDA(ctx, cudaEventRecord(ctx->ev_x_ready, ctx->stream));
+    BH_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x_ready, 0));
+    ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm2);
+    BH_NCCL(ctx, g_nccl.GroupStart());
+    for (const auto& r : ctx->halo_send)
+        BH_NCCL(ctx, g_nccl.Send(x_local + (r.off - ctx->row0), (size_t)r.count, ncclDouble, r.peer, comm, ctx->comm_stream));
+    for (const auto& r : ctx->halo_recv)
+        BH_NCCL(ctx, g_nccl.Recv(ctx->d_xfull + r.off, (size_t)r.count, ncclDouble, r.peer, comm, ctx->comm_stream));
+    BH_NCCL(ctx, g_nccl.GroupEnd());
+    BH_CUDA(ctx, cudaEventRecord(ctx->ev_halo_done, ctx->comm_stream));
+    return BH_OK;
+}
+
+int bh_dist_halo_end(bh_ctx* ctx)
+{
+    BH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo_done, 0));
     return BH_OK;
 }

@@ -382,6 +382,100 @@ k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, cons
     }
 }
 
+// Row-partitioned form of the chain kernel (one large eigensolve over several GPUs, BASELINE.json config 5): the hops of a
+// row are split by where their source element lives.  PHASE 1 takes the hops whose source is in this rank's own slice
+// [row0, row0 + D) -- x is then the LOCAL slice, addressed through a pointer shifted by -row0 -- plus the diagonal and the
+// epilogue, and runs while the halo exchange is in flight; PHASE 2 adds the hops whose source lies in another rank's slice
+// from the exchanged full-length buffer.  Both are the single sweep of k_hv_free_chain with a range test per hop.
+template <int M, bool CLOSED, int PHASE>
+__global__ void __launch_bounds__(256, CHAIN_MIN_BLOCKS)
+k_hv_free_chain_part(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
+                     const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
+                     double* __restrict__ y, BhEpilogue ep)
+{
+    __shared__ BhTables t;
+    bh_stage_tables(&t, gtab);
+    const double shift = __dmul_rn(-(double)t.n, cmu);
+    const unsigned lo = (unsigned)row0, len = (unsigned)D;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = row0 + l;
+        const uint64_t s = states[l];
+        const int kk = (int)k;
+        const int n0 = bh_occ(s, 0);
+        int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
+        double acc = 0.0;
+        auto hop = [&](int cond, int tgt, double amp) {
+            const bool local = ((unsigned)tgt - lo) < len;
+            const bool take = cond && (PHASE == 1 ? local : !local);
+            const double xv = take ? __ldg(x + tgt) : 0.0;
+            acc = fma(amp, xv, acc);
+        };
+#pragma unroll
+        for (int q = 0; q < M - 1; ++q) {
+            const int nnext = bh_occ(s, q + 1);
+            const int2 gh = t.gh[q][R];
+            hop(nnext, kk + gh.x, t.sq[(nprev + 1) * nnext]);
+            hop(nprev, kk + gh.y, t.sq[(nnext + 1) * nprev]);
+            tdn += gh.x;
+            tup += gh.y;
+            R -= nnext;
+            nprev = nnext;
+        }
+        if (CLOSED) {
+            const int nl = nprev;
+            hop(nl, kk + tdn, t.sq[(n0 + 1) * nl]);
+            hop(n0, kk + tup, t.sq[(nl + 1) * n0]);
+        }
+        if (PHASE == 1) {
+            const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
+            const double xv = x[k];
+            double out = ep.s1 * (diag * xv - (2.0 * cJ) * acc);
+            if (ep.s2 != 0.0) out = fma(ep.s2, xv, out);
+            if (ep.z) out = fma(ep.s3, ep.z[l], out);
+            y[l] = out;
+        } else if (acc != 0.0) {
+            y[l] = fma(ep.s1 * (-2.0 * cJ), acc, y[l]);
+        }
+    }
+}
+
+// Which 4096-row chunks of the global vector hold a source element of some hop of this rank's rows: flags[chunk] = 1
+// (the halo plan of dist.cu is built from these flags once per bh_setup_partitioned).
+#define HALO_CHUNK_SHIFT 12
+template <int M, bool CLOSED>
+__global__ void __launch_bounds__(256)
+k_mark_halo_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
+                  unsigned char* __restrict__ flags)
+{
+    __shared__ BhTables t;
+    bh_stage_tables(&t, gtab);
+    const unsigned lo = (unsigned)row0, len = (unsigned)D;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = states[l];
+        const int kk = (int)(row0 + l);
+        const int n0 = bh_occ(s, 0);
+        int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
+        auto mark = [&](int cond, int tgt) {
+            if (cond && !(((unsigned)tgt - lo) < len)) flags[tgt >> HALO_CHUNK_SHIFT] = 1;
+        };
+#pragma unroll
+        for (int q = 0; q < M - 1; ++q) {
+            const int nnext = bh_occ(s, q + 1);
+            const int2 gh = t.gh[q][R];
+            mark(nnext, kk + gh.x);
+            mark(nprev, kk + gh.y);
+            tdn += gh.x;
+            tup += gh.y;
+            R -= nnext;
+            nprev = nnext;
+        }
+        if (CLOSED) {
+            mark(nprev, kk + tdn);
+            mark(n0, kk + tup);
+        }
+    }
+}
+
 template <bool CLOSED>
 static hv_free_fn_t hv_chain_kernel(int m)
 {
@@ -511,6 +605,64 @@ static hv_hybrid_fn_t hv_hybrid_kernel(int m)
         case 16: return k_hv_hybrid<16, CLOSED>;
     }
     return nullptr;
+}
+
+template <bool CLOSED, int PHASE>
+static hv_free_fn_t hv_chain_part_kernel(int m)
+{
+    switch (m) {
+        case 3: return k_hv_free_chain_part<3, CLOSED, PHASE>;
+        case 4: return k_hv_free_chain_part<4, CLOSED, PHASE>;
+        case 5: return k_hv_free_chain_part<5, CLOSED, PHASE>;
+        case 6: return k_hv_free_chain_part<6, CLOSED, PHASE>;
+        case 7: return k_hv_free_chain_part<7, CLOSED, PHASE>;
+        case 8: return k_hv_free_chain_part<8, CLOSED, PHASE>;
+        case 9: return k_hv_free_chain_part<9, CLOSED, PHASE>;
+        case 10: return k_hv_free_chain_part<10, CLOSED, PHASE>;
+        case 11: return k_hv_free_chain_part<11, CLOSED, PHASE>;
+        case 12: return k_hv_free_chain_part<12, CLOSED, PHASE>;
+        case 13: return k_hv_free_chain_part<13, CLOSED, PHASE>;
+        case 14: return k_hv_free_chain_part<14, CLOSED, PHASE>;
+        case 15: return k_hv_free_chain_part<15, CLOSED, PHASE>;
+        case 16: return k_hv_free_chain_part<16, CLOSED, PHASE>;
+    }
+    return nullptr;
+}
+
+typedef void (*mark_fn_t)(const BhTables*, int64_t, int64_t, const uint64_t*, unsigned char*);
+template <bool CLOSED>
+static mark_fn_t mark_halo_kernel(int m)
+{
+    switch (m) {
+        case 3: return k_mark_halo_chain<3, CLOSED>;
+        case 4: return k_mark_halo_chain<4, CLOSED>;
+        case 5: return k_mark_halo_chain<5, CLOSED>;
+        case 6: return k_mark_halo_chain<6, CLOSED>;
+        case 7: return k_mark_halo_chain<7, CLOSED>;
+        case 8: return k_mark_halo_chain<8, CLOSED>;
+        case 9: return k_mark_halo_chain<9, CLOSED>;
+        case 10: return k_mark_halo_chain<10, CLOSED>;
+        case 11: return k_mark_halo_chain<11, CLOSED>;
+        case 12: return k_mark_halo_chain<12, CLOSED>;
+        case 13: return k_mark_halo_chain<13, CLOSED>;
+        case 14: return k_mark_halo_chain<14, CLOSED>;
+        case 15: return k_mark_halo_chain<15, CLOSED>;
+        case 16: return k_mark_halo_chain<16, CLOSED>;
+    }
+    return nullptr;
+}
+
+// flags_dev[(world * ld) >> 12 chunks] <- 1 where this rank's rows read a remote chunk (chains only); see dist.cu
+int bh_mark_halo_chunks(bh_ctx* ctx, unsigned char* flags_dev)
+{
+    if (!ctx->h_tab.chain || ctx->m < 3) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "halo plan: chains only");
+    if (ctx->nloc == 0) return BH_OK;
+    mark_fn_t fn = (ctx->h_tab.chain == 2) ? mark_halo_kernel<true>(ctx->m) : mark_halo_kernel<false>(ctx->m);
+    const int grid = (int)std::min<int64_t>(nblocks(ctx->nloc, 256), (int64_t)ctx->sm_count * 8);
+    fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, ctx->nloc, ctx->d_states, flags_dev);
+    BH_LAUNCHED(ctx);
+    BH_CUDA(ctx, cudaGetLastError());
+    return BH_OK;
 }
 
 typedef void (*hv_free_fn)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double, double, double,
@@ -710,6 +862,25 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
         // row-partitioned context: x is the local slice; exchange it (NCCL all-gather) and read the full vector
         const double* xin = x;
         const int64_t nloc = ctx->nloc;
+        if (ctx->partitioned && ctx->halo_ready && ctx->h_tab.chain && ctx->m >= 3) {
+            // overlapped form: halo exchange on the communication stream, own-slice hops meanwhile, remote hops afterwards
+            BH_TRY(bh_dist_halo_begin(ctx, x));
+            const bool closed = ctx->h_tab.chain == 2;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8));
+            if (nloc > 0) {
+                hv_free_fn_t f1 = closed ? hv_chain_part_kernel<true, 1>(ctx->m) : hv_chain_part_kernel<false, 1>(ctx->m);
+                f1<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x - ctx->row0, y, ep);
+                BH_LAUNCHED(ctx);
+            }
+            BH_TRY(bh_dist_halo_end(ctx));
+            if (nloc > 0) {
+                hv_free_fn_t f2 = closed ? hv_chain_part_kernel<true, 2>(ctx->m) : hv_chain_part_kernel<false, 2>(ctx->m);
+                f2<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, ctx->d_xfull, y, ep);
+                BH_LAUNCHED(ctx);
+            }
+            BH_CUDA(ctx, cudaGetLastError());
+            return BH_OK;
+        }
         if (ctx->partitioned) {
             BH_TRY(bh_dist_allgather(ctx, x, ctx->d_xfull, ctx->ld));
             xin = ctx->d_xfull;

@@ -90,7 +90,7 @@ def test_points(pkg, ctx_factory, key):
         got = ctx.point(cJ, cU, cu, kernel=kernel)
         assert np.all(np.abs(got["evals"] - want) <= 1e-10 * scale), (kernel, got["evals"] - want)
         assert np.abs(got["rho"] - rho).max() <= 1e-10 * np.abs(rho).max(), kernel
-        assert_out3(got["out3"], G[f"point_{key}_out5"][2:], want, got["evals"])   # see parity_util: degenerate tori
+        assert_out3(got["out3"], G[f"point_{key}_out5"][2:], want, got["evals"])   # see parity_util (gap-ratio conditioning)
 
 
 @pytest.mark.parametrize("m,n,lx,ly", [(6, 4, 3, 2), (8, 6, 4, 2), (12, 3, 4, 3)])
