@@ -25,7 +25,7 @@ SYMBOLS = [
     "bh_term_nnz", "bh_term_csc", "bh_hamiltonian_nnz", "bh_hamiltonian_csc", "bh_hv", "bh_hv_dev", "bh_eigs",
     "bh_spdm", "bh_gap_ratios", "bh_condensate_fraction", "bh_coherence", "bh_point", "bh_points",
     "bh_lcg_fill_dev", "bh_hv_algorithmic_bytes", "bh_load_matrix", "bh_ctx_set_batch",
-    "bh_ctx_profile_enable", "bh_ctx_profile_read",
+    "bh_ctx_profile_enable", "bh_ctx_profile_read", "bh_host_register", "bh_host_unregister",
     "bh_dist_unique_id", "bh_dist_init", "bh_dist_finalize", "bh_setup_partitioned", "bh_partition",
 ]
 
@@ -85,6 +85,8 @@ def load():
     L.bh_point.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, C.POINTER(EigsInfo)]
     L.bh_points.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
     L.bh_ctx_set_batch.argtypes = [vp, C.c_int]
+    L.bh_host_register.argtypes = [vp, C.c_int64]
+    L.bh_host_unregister.argtypes = [vp]
     L.bh_ctx_profile_enable.argtypes = [vp, C.c_int]
     L.bh_ctx_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), dp, dp]
     L.bh_dist_unique_id.argtypes = [vp]
@@ -101,6 +103,15 @@ def load():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def host_register(a):
+    """Page-lock a numpy array owned by the caller (bh_host_register); returns True on success."""
+    return load().bh_host_register(_ptr(a), a.nbytes) == OK
+
+
+def host_unregister(a):
+    return load().bh_host_unregister(_ptr(a)) == OK
 
 
 def dimension(m, n):

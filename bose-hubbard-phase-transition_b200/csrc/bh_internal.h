@@ -83,6 +83,12 @@ struct bh_ctx {
     cudaEvent_t ev_x_ready = nullptr, ev_halo_done = nullptr;
     bool halo_ready = false;
     int64_t halo_recv_elems = 0;
+    // the hops of this rank's rows whose source element lives in another rank's slice, stored once as a CSR matrix
+    // (pattern and amplitudes are fixed by the basis and the partition; 2J is applied at run time)
+    int* d_rem_ptr = nullptr;     // [nloc + 1]
+    int* d_rem_col = nullptr;     // global LEX rank of the source
+    double* d_rem_amp = nullptr;  // sqrt((n_dst + 1) n_src)
+    int64_t rem_nnz = 0;
     std::vector<int> nbr_ptr, nbr_idx;
     BhTables h_tab;
     BhTables* d_tab = nullptr;
@@ -133,6 +139,7 @@ struct bh_ctx {
     int* d_inv_tag = nullptr;
 
     int cheb_degree = 8;   // Chebyshev filter degree of the accelerated solver (1 = plain Lanczos; env BH_CHEB_DEGREE)
+    int cheb_quick = 24;   // quick stage 1 for D >= 50000: one cycle of this many plain steps locates E_0 (0 = always the full stage 1; env BH_CHEB_QUICK)
     int cheb_pre = 3;      // plain restart cycles run first to locate the wanted end of the spectrum (env BH_CHEB_PRE)
     double cheb_margin = 0.05;  // cut >= theta_{nev-1} + margin * (theta_{nev-1} - theta_0)   (env BH_CHEB_MARGIN)
     double cheb_frac = 0.08;    // cut >= theta_0 + frac * (hi - theta_0)                       (env BH_CHEB_FRAC)
@@ -256,6 +263,8 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
 int bh_dist_allreduce_sum(bh_ctx* ctx, double* buf_dev, int64_t count);
 int bh_dist_allgather(bh_ctx* ctx, const double* send_dev, double* recv_dev, int64_t count_per_rank);
 int bh_mark_halo_chunks(bh_ctx* ctx, unsigned char* flags_dev);  // hv.cu
+int bh_build_remote_hops(bh_ctx* ctx);                           // hv.cu: d_rem_* (chains, partitioned)
+int bh_exclusive_scan(bh_ctx* ctx, int64_t n, const int* d_in, int* d_out, int64_t* total);  // csr.cu: out[0..n]
 int bh_dist_plan_halo(bh_ctx* ctx);                              // once per bh_setup_partitioned (chains)
 int bh_dist_halo_begin(bh_ctx* ctx, const double* x_local);      // start the exchange of x into d_xfull (communication stream)
 int bh_dist_halo_end(bh_ctx* ctx);                               // the context's stream waits for it

@@ -90,7 +90,7 @@ __global__ void k_scan_add(int64_t n, int* __restrict__ out, const long long* __
 }
 
 // out[0..n] = exclusive prefix sums of in[0..n); returns the total
-static int exclusive_scan(bh_ctx* ctx, int64_t n, const int* d_in, int* d_out, int64_t* total)
+int bh_exclusive_scan(bh_ctx* ctx, int64_t n, const int* d_in, int* d_out, int64_t* total)
 {
     const int nb = nblocks(n, SCAN_THREADS * SCAN_ITEMS);
     long long* d_bsum = nullptr;
@@ -200,7 +200,7 @@ int bh_build_hamiltonian(bh_ctx* ctx)
     k_row_count<<<nblocks(D, 256), 256, 0, ctx->stream>>>(ctx->d_tab, D, ctx->d_states, d_len);
     BH_LAUNCHED(ctx);
     int64_t total = 0;
-    BH_TRY(exclusive_scan(ctx, D, d_len, ctx->d_rowptr, &total));
+    BH_TRY(bh_exclusive_scan(ctx, D, d_len, ctx->d_rowptr, &total));
     cudaFree(d_len);
     if (total >= ((int64_t)1 << 31))
         return bh_fail(ctx, BH_ERR_UNSUPPORTED, "stored Hamiltonian has >= 2^31 entries; use the matrix-free kernel");
@@ -358,7 +358,7 @@ static int build_sell(bh_ctx* ctx)
     k_sell_sizes<<<nblocks(ns, 256), 256, 0, ctx->stream>>>(ns, ctx->d_rowptr, ctx->d_sell_row, d_sizes);
     ctx->launches += 2;
     int64_t total = 0;
-    BH_TRY(exclusive_scan(ctx, ns, d_sizes, ctx->d_sell_ptr, &total));
+    BH_TRY(bh_exclusive_scan(ctx, ns, d_sizes, ctx->d_sell_ptr, &total));
     cudaFree(d_sizes);
     if (total >= ((int64_t)1 << 31)) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "SELL copy has >= 2^31 entries");
     ctx->sell_nslices = ns;
@@ -494,7 +494,7 @@ static int export_matrix(bh_ctx* ctx, int mode, double cJ, double cU, double cmu
     k_export_len<<<nblocks(D, 256), 256, 0, ctx->stream>>>(D, ctx->d_rowptr, perm, mode, d_len);
     BH_LAUNCHED(ctx);
     int64_t total = 0;
-    BH_TRY(exclusive_scan(ctx, D, d_len, d_outer, &total));
+    BH_TRY(bh_exclusive_scan(ctx, D, d_len, d_outer, &total));
     if (total != nnz) return bh_fail(ctx, BH_ERR_STATE, "export: inconsistent entry count");
     k_export_rows<<<nblocks(D, 128), 128, 0, ctx->stream>>>(D, ctx->n, ctx->d_rowptr, ctx->d_col, ctx->d_valJ, ctx->d_dU,
                                                              perm, inv, mode, cJ, cU, cmu, d_outer, d_inner, d_val);

@@ -79,6 +79,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     if (const char* v = getenv("BH_COMPRESS_TILED")) ctx->compress_tiled = atoi(v);
     if (const char* v = getenv("BH_CHEB_DEGREE")) ctx->cheb_degree = std::max(1, atoi(v));
     if (const char* v = getenv("BH_CHEB_PRE")) ctx->cheb_pre = std::max(1, atoi(v));
+    if (const char* v = getenv("BH_CHEB_QUICK")) ctx->cheb_quick = std::max(0, atoi(v));
     if (const char* v = getenv("BH_CHEB_MARGIN")) ctx->cheb_margin = atof(v);
     if (const char* v = getenv("BH_CHEB_FRAC")) ctx->cheb_frac = atof(v);
     if (const char* v = getenv("BH_REORTH_BLOCK")) { ctx->reorth_block = std::min(BH_MAX_NCV, std::max(1, atoi(v))); ctx->reorth_block_forced = true; }

@@ -89,6 +89,12 @@ extern "C" int bh_dist_init(bh_ctx* ctx, int world, int rank, const void* id128)
 
 void bh_dist_release_halo(bh_ctx* ctx)
 {
+    if (ctx->d_rem_ptr) cudaFree(ctx->d_rem_ptr);
+    if (ctx->d_rem_col) cudaFree(ctx->d_rem_col);
+    if (ctx->d_rem_amp) cudaFree(ctx->d_rem_amp);
+    ctx->d_rem_ptr = ctx->d_rem_col = nullptr;
+    ctx->d_rem_amp = nullptr;
+    ctx->rem_nnz = 0;
     ctx->halo_ready = false;
     ctx->halo_send.clear();
     ctx->halo_recv.clear();
@@ -171,7 +177,9 @@ int bh_dist_plan_halo(bh_ctx* ctx)
         ncclComm_t c2;
         BH_NCCL(ctx, g_nccl.CommSplit(static_cast<ncclComm_t>(ctx->nccl_comm), 0, ctx->rank, &c2, nullptr));
         ctx->nccl_comm2 = c2;
-        BH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        BH_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        BH_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
         BH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_x_ready, cudaEventDisableTiming));
         BH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo_done, cudaEventDisableTiming));
     }
@@ -215,10 +223,13 @@ int bh_dist_plan_halo(bh_ctx* ctx)
     }
     ctx->halo_recv_elems = 0;
     for (const auto& r : ctx->halo_recv) ctx->halo_recv_elems += r.count;
+    BH_TRY(bh_build_remote_hops(ctx));
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->halo_ready = true;
     if (getenv("BH_DIST_VERBOSE"))
-        fprintf(stderr, "[bh] rank %d halo plan: %zu recv ranges (%.1f MB = %.3f D), %zu send ranges\n", ctx->rank, ctx->halo_recv.size(),
-                ctx->halo_recv_elems * 8e-6, (double)ctx->halo_recv_elems / (double)ctx->D, ctx->halo_send.size());
+        fprintf(stderr, "[bh] rank %d halo plan: %zu recv ranges (%.1f MB = %.3f D), %zu send ranges, %.2f remote hops per row\n", ctx->rank,
+                ctx->halo_recv.size(), ctx->halo_recv_elems * 8e-6, (double)ctx->halo_recv_elems / (double)ctx->D, ctx->halo_send.size(),
+                (double)ctx->rem_nnz / (double)std::max<int64_t>(ctx->nloc, 1));
     return BH_OK;
 }
 

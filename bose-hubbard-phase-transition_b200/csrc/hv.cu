@@ -652,6 +652,119 @@ static mark_fn_t mark_halo_kernel(int m)
     return nullptr;
 }
 
+// The remote hops of every local row as a CSR matrix (built once per bh_setup_partitioned): MODE 0 counts them per row,
+// MODE 1 writes (source rank, amplitude) at the scanned offsets, in the order of the sweep.
+template <int M, bool CLOSED, int MODE>
+__global__ void __launch_bounds__(256)
+k_remote_hops(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
+              int* __restrict__ ptr_or_count, int* __restrict__ col, double* __restrict__ amp)
+{
+    __shared__ BhTables t;
+    bh_stage_tables(&t, gtab);
+    const unsigned lo = (unsigned)row0, len = (unsigned)D;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = states[l];
+        const int kk = (int)(row0 + l);
+        const int n0 = bh_occ(s, 0);
+        int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
+        int pos = (MODE == 1) ? ptr_or_count[l] : 0;
+        auto hop = [&](int cond, int tgt, int code) {
+            if (cond && !(((unsigned)tgt - lo) < len)) {
+                if (MODE == 1) {
+                    col[pos] = tgt;
+                    amp[pos] = t.sq[code];
+                }
+                ++pos;
+            }
+        };
+#pragma unroll
+        for (int q = 0; q < M - 1; ++q) {
+            const int nnext = bh_occ(s, q + 1);
+            const int2 gh = t.gh[q][R];
+            hop(nnext, kk + gh.x, (nprev + 1) * nnext);
+            hop(nprev, kk + gh.y, (nnext + 1) * nprev);
+            tdn += gh.x;
+            tup += gh.y;
+            R -= nnext;
+            nprev = nnext;
+        }
+        if (CLOSED) {
+            const int nl = nprev;
+            hop(nl, kk + tdn, (n0 + 1) * nl);
+            hop(n0, kk + tup, (nl + 1) * n0);
+        }
+        if (MODE == 0) ptr_or_count[l] = pos;
+    }
+}
+
+// y[l] += coef * sum_e amp[e] x[col[e]] over the remote hops of row l (x = the exchanged full-length buffer)
+__global__ void __launch_bounds__(256)
+k_hv_remote(int64_t D, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ amp,
+            const double* __restrict__ x, double* __restrict__ y, double coef)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= D) return;
+    const int a = __ldg(ptr + l), b = __ldg(ptr + l + 1);
+    if (a == b) return;
+    double acc = 0.0;
+    for (int e = a; e < b; ++e) acc = fma(__ldcs(amp + e), __ldg(x + __ldcs(col + e)), acc);
+    y[l] = fma(coef, acc, y[l]);
+}
+
+typedef void (*remote_fn_t)(const BhTables*, int64_t, int64_t, const uint64_t*, int*, int*, double*);
+template <bool CLOSED, int MODE>
+static remote_fn_t remote_hops_kernel(int m)
+{
+    switch (m) {
+        case 3: return k_remote_hops<3, CLOSED, MODE>;
+        case 4: return k_remote_hops<4, CLOSED, MODE>;
+        case 5: return k_remote_hops<5, CLOSED, MODE>;
+        case 6: return k_remote_hops<6, CLOSED, MODE>;
+        case 7: return k_remote_hops<7, CLOSED, MODE>;
+        case 8: return k_remote_hops<8, CLOSED, MODE>;
+        case 9: return k_remote_hops<9, CLOSED, MODE>;
+        case 10: return k_remote_hops<10, CLOSED, MODE>;
+        case 11: return k_remote_hops<11, CLOSED, MODE>;
+        case 12: return k_remote_hops<12, CLOSED, MODE>;
+        case 13: return k_remote_hops<13, CLOSED, MODE>;
+        case 14: return k_remote_hops<14, CLOSED, MODE>;
+        case 15: return k_remote_hops<15, CLOSED, MODE>;
+        case 16: return k_remote_hops<16, CLOSED, MODE>;
+    }
+    return nullptr;
+}
+
+int bh_build_remote_hops(bh_ctx* ctx)
+{
+    if (ctx->d_rem_ptr) { cudaFree(ctx->d_rem_ptr); ctx->d_rem_ptr = nullptr; }
+    if (ctx->d_rem_col) { cudaFree(ctx->d_rem_col); ctx->d_rem_col = nullptr; }
+    if (ctx->d_rem_amp) { cudaFree(ctx->d_rem_amp); ctx->d_rem_amp = nullptr; }
+    ctx->rem_nnz = 0;
+    const int64_t nloc = ctx->nloc;
+    const bool closed = ctx->h_tab.chain == 2;
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_rem_ptr, sizeof(int) * (size_t)(nloc + 1)));
+    BH_CUDA(ctx, cudaMemsetAsync(ctx->d_rem_ptr, 0, sizeof(int) * (size_t)(nloc + 1), ctx->stream));
+    if (nloc == 0) return BH_OK;
+    int* d_cnt = nullptr;
+    BH_CUDA(ctx, cudaMalloc(&d_cnt, sizeof(int) * (size_t)nloc));
+    const int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
+    remote_fn_t f0 = closed ? remote_hops_kernel<true, 0>(ctx->m) : remote_hops_kernel<false, 0>(ctx->m);
+    f0<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, d_cnt, nullptr, nullptr);
+    BH_LAUNCHED(ctx);
+    int64_t total = 0;
+    BH_TRY(bh_exclusive_scan(ctx, nloc, d_cnt, ctx->d_rem_ptr, &total));
+    cudaFree(d_cnt);
+    if (total >= ((int64_t)1 << 31)) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "remote hop matrix: more than 2^31 entries");
+    ctx->rem_nnz = total;
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_rem_col, sizeof(int) * (size_t)std::max<int64_t>(total, 1)));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_rem_amp, sizeof(double) * (size_t)std::max<int64_t>(total, 1)));
+    remote_fn_t f1 = closed ? remote_hops_kernel<true, 1>(ctx->m) : remote_hops_kernel<false, 1>(ctx->m);
+    f1<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_rem_ptr, ctx->d_rem_col, ctx->d_rem_amp);
+    BH_LAUNCHED(ctx);
+    BH_CUDA(ctx, cudaGetLastError());
+    return BH_OK;
+}
+
 // flags_dev[(world * ld) >> 12 chunks] <- 1 where this rank's rows read a remote chunk (chains only); see dist.cu
 int bh_mark_halo_chunks(bh_ctx* ctx, unsigned char* flags_dev)
 {
@@ -864,18 +977,21 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
         const int64_t nloc = ctx->nloc;
         if (ctx->partitioned && ctx->halo_ready && ctx->h_tab.chain && ctx->m >= 3) {
             // overlapped form: halo exchange on the communication stream, own-slice hops meanwhile, remote hops afterwards
-            BH_TRY(bh_dist_halo_begin(ctx, x));
+            static const int ablate = getenv("BH_HALO_ABLATE") ? atoi(getenv("BH_HALO_ABLATE")) : 0;  // timing probes only
+            if (!(ablate & 1)) BH_TRY(bh_dist_halo_begin(ctx, x));
             const bool closed = ctx->h_tab.chain == 2;
-            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8));
-            if (nloc > 0) {
+            // one CTA per 256 rows (not a persistent grid): the exchange kernel on the high-priority communication stream
+            // gets its SM slots as soon as the first CTAs retire, so that the two really overlap
+            const int grid = (int)std::max<int64_t>(1, nblocks(nloc, 256));
+            if (nloc > 0 && !(ablate & 2)) {
                 hv_free_fn_t f1 = closed ? hv_chain_part_kernel<true, 1>(ctx->m) : hv_chain_part_kernel<false, 1>(ctx->m);
                 f1<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x - ctx->row0, y, ep);
                 BH_LAUNCHED(ctx);
             }
-            BH_TRY(bh_dist_halo_end(ctx));
-            if (nloc > 0) {
-                hv_free_fn_t f2 = closed ? hv_chain_part_kernel<true, 2>(ctx->m) : hv_chain_part_kernel<false, 2>(ctx->m);
-                f2<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, ctx->d_xfull, y, ep);
+            if (!(ablate & 1)) BH_TRY(bh_dist_halo_end(ctx));
+            if (nloc > 0 && !(ablate & 4) && ctx->rem_nnz > 0) {
+                k_hv_remote<<<grid, 256, 0, ctx->stream>>>(nloc, ctx->d_rem_ptr, ctx->d_rem_col, ctx->d_rem_amp, ctx->d_xfull, y,
+                                                           ep.s1 * (-2.0 * cJ));
                 BH_LAUNCHED(ctx);
             }
             BH_CUDA(ctx, cudaGetLastError());
@@ -942,6 +1058,18 @@ extern "C" int bh_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, 
     BH_D2H(ctx, y, ctx->d_y, bytes);
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BH_OK;
+}
+
+extern "C" int bh_host_register(void* ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return BH_ERR_ARG;
+    return cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? BH_OK : BH_ERR_CUDA;
+}
+
+extern "C" int bh_host_unregister(void* ptr)
+{
+    if (!ptr) return BH_ERR_ARG;
+    return cudaHostUnregister(ptr) == cudaSuccess ? BH_OK : BH_ERR_CUDA;
 }
 
 extern "C" int bh_hv_algorithmic_bytes(bh_ctx* ctx, int kernel, int64_t* bytes)

@@ -1125,69 +1125,47 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
     return BH_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Solver driver.  Plain mode (cheb_degree = 1) is the reference's algorithm step for step.  The accelerated
-// mode runs the same thick-restart Lanczos on a Chebyshev polynomial of H:
-//   stage 1  a few plain restart cycles give Ritz values theta_0 <= ... (upper bounds of the eigenvalues by
-//            interlacing), so cut = theta_{nev-1} + margin is guaranteed to lie above the nev wanted levels;
-//   stage 2  Lanczos on B = -/+T_d((H - c)/e), [cut, hi] -> [-1, 1] with hi the Gershgorin bound: the wanted end
-//            is amplified like cosh(d acosh(.)) and every Lanczos step (one re-orthogonalisation against the
-//            basis, the dominant cost) advances the Krylov polynomial by d degrees.  The d applications of H use
-//            the fused epilogue of the H.v kernels (no extra vector passes);
-//   stage 3  Rayleigh-Ritz of H itself on the final basis (ncv H.v + ncv multi-dots, host 41 x 41 eigenproblem):
-//            eigenvalues and vectors of H, not of the polynomial.
-// Measured (numpy model, m=n=8): d = 7 needs 4.5x fewer Lanczos steps for 1.4-1.6x more H.v; eigenvalues agree
-// with the plain solver to 1e-12.
-// ---------------------------------------------------------------------------------------------------------
-int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
-               BhSolve* out)
+// One attempt of the accelerated solve (see bh_lanczos).  *retry = true: the quick stage 1 misplaced the cut, run the full form.
+static int accel_solve(bh_ctx* ctx, const LanczosOp& plain, int& hv_count, double cJ, double cU, double cmu, int nev, int ncv, double tol,
+                       int maxit, int kernel, bool quick, bool* retry, BhSolve* out)
 {
-    const auto t_start = std::chrono::steady_clock::now();
-    int hv_count = 0;
-    LanczosOp plain = [&](const double* x, double* y) {
-        ++hv_count;
-        if (ctx->parent && ctx->parent->hub && ctx->parent->batch_plain) {
-            // lockstep solve: a plain H.v is a filter request of degree 1 with c = 0, e = 1 (s1 = 1, s2 = -0 is skipped)
-            bool handled = false;
-            BH_TRY(bh_batch_filter(ctx, x, y, 0.0, 1.0, cJ, cU, cmu, 1, &handled));
-            if (handled) return (int)BH_OK;
-        }
-        return bh_launch_hv(ctx, cJ, cU, cmu, kernel, x, y);
-    };
     const int d = ctx->cheb_degree;
-    const bool accel = d > 1 && !ctx->user_matrix && kernel != BH_HV_USER && ctx->D >= 2000 && ncv >= nev + 2 && ncv <= ctx->D;
-    if (!accel) {
-        const int rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
-        out->info.nmatvec = hv_count;
-        return rc;
-    }
+    *retry = false;
     // ---- stage 1 ----
     BhSolve s1;
-    int rc = lanczos_core(ctx, plain, false, nev, ncv, tol, std::min(maxit, ctx->cheb_pre), &s1);
-    if (rc != BH_ERR_NOCONV || (int)s1.evals.size() < nev) {  // converged already, or a real error
-        *out = s1;
-        out->info.nmatvec = hv_count;
-        return rc;
+    int rc;
+    if (quick) {
+        rc = lanczos_core(ctx, plain, false, 1, ctx->cheb_quick, tol, 0, &s1);
+        if (rc != BH_ERR_NOCONV && rc != BH_OK) return rc;
+    } else {
+        rc = lanczos_core(ctx, plain, false, nev, ncv, tol, std::min(maxit, ctx->cheb_pre), &s1);
+        if (rc != BH_ERR_NOCONV || (int)s1.evals.size() < nev) {  // converged already, or a real error
+            *out = s1;
+            out->info.nmatvec = hv_count;
+            return rc;
+        }
     }
     double lo = 0, hi = 0;
     BH_TRY(bh_spectrum_bounds(ctx, cJ, cU, cmu, &lo, &hi));
-    const double th0 = s1.evals[0], thn = s1.evals[nev - 1];
+    const double th0 = s1.evals[0], thn = quick ? s1.evals[0] : s1.evals[nev - 1];
     hi += 1e-9 * (hi - lo) + 1e-12;
     double cut = std::max(thn + ctx->cheb_margin * (thn - th0), th0 + ctx->cheb_frac * (hi - th0));
     if (!(cut < th0 + 0.8 * (hi - th0))) {  // no room for a filter: finish with the plain solver
+        if (quick) { *retry = true; return BH_OK; }
         rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
         out->info.nmatvec = hv_count;
         return rc;
     }
     const double c = 0.5 * (hi + cut), e = 0.5 * (hi - cut);
-    // start vector of stage 2: the sum of the stage-1 Ritz vectors of the wanted end
+    // start vector of stage 2: the sum of the stage-1 Ritz vectors of the wanted end (quick: the ground Ritz vector)
     {
-        std::vector<double> ysum(ncv, 0.0);
-        for (int l = 0; l < nev; ++l)
-            for (int r = 0; r < ncv; ++r) ysum[r] += s1.Y[r + (size_t)l * ncv];
-        BH_H2D(ctx, ctx->d_small, ysum.data(), sizeof(double) * ncv);
+        const int n1 = s1.ncv, take = quick ? 1 : nev;
+        std::vector<double> ysum(n1, 0.0);
+        for (int l = 0; l < take; ++l)
+            for (int r = 0; r < n1; ++r) ysum[r] += s1.Y[r + (size_t)l * n1];
+        BH_H2D(ctx, ctx->d_small, ysum.data(), sizeof(double) * n1);
         const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(ctx->nloc, VEC_THREADS), (int64_t)ctx->sm_count * 4));
-        k_lincomb<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->nloc, ctx->ld, ctx->d_V, ncv, ctx->d_small, ctx->d_w);
+        k_lincomb<<<G, VEC_THREADS, 0, ctx->stream>>>(ctx->nloc, ctx->ld, ctx->d_V, n1, ctx->d_small, ctx->d_w);
         BH_LAUNCHED(ctx);
     }
     for (int q = 0; q < 3; ++q)
@@ -1228,8 +1206,12 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
         return (int)BH_OK;
     };
     BhSolve s2;
-    rc = lanczos_core(ctx, cheb, true, nev, ncv, tol, maxit, &s2);
+    rc = lanczos_core(ctx, cheb, true, nev, ncv, tol, quick ? std::min(maxit, 80) : maxit, &s2);
     const int restarts = s1.info.nrestart + s2.info.nrestart;
+    if (rc == BH_ERR_NOCONV && quick) {  // a misplaced cut stalls the filtered iteration: full stage 1
+        *retry = true;
+        return BH_OK;
+    }
     if (rc == BH_ERR_NOCONV) {  // the filtered iteration stalled: fall back to the reference algorithm
         rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
         out->info.nmatvec = hv_count;
@@ -1282,6 +1264,10 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
                 M[a + (size_t)b * ncv] = M[b + (size_t)a * ncv] = v;
             }
         bh_sym_eig(ncv, M, evH, Z);
+        if (quick && !(evH[nev - 1] < cut - 0.02 * (cut - evH[0]))) {  // the cut was not safely above the nev-th level
+            *retry = true;
+            return BH_OK;
+        }
         if (!(evH[nev - 1] < cut)) {
             // the wanted levels were not all below the cut (cannot happen by interlacing; kept as a safety net)
             rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
@@ -1298,8 +1284,64 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
     out->info.nmatvec = hv_count;
     out->info.nrestart = restarts;
     out->info.nreorth = s1.info.nreorth + s2.info.nreorth;
-    out->info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     return BH_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Solver driver.  Plain mode (cheb_degree = 1) is the reference's algorithm step for step.  The accelerated
+// mode runs the same thick-restart Lanczos on a Chebyshev polynomial of H:
+//   stage 1  a few plain restart cycles give Ritz values theta_0 <= ... (upper bounds of the eigenvalues by
+//            interlacing), so cut = theta_{nev-1} + margin is guaranteed to lie above the nev wanted levels;
+//   stage 2  Lanczos on B = -/+T_d((H - c)/e), [cut, hi] -> [-1, 1] with hi the Gershgorin bound: the wanted end
+//            is amplified like cosh(d acosh(.)) and every Lanczos step (one re-orthogonalisation against the
+//            basis, the dominant cost) advances the Krylov polynomial by d degrees.  The d applications of H use
+//            the fused epilogue of the H.v kernels (no extra vector passes);
+//   stage 3  Rayleigh-Ritz of H itself on the final basis (ncv H.v + ncv multi-dots, host 41 x 41 eigenproblem):
+//            eigenvalues and vectors of H, not of the polynomial.
+// Measured (numpy model, m=n=8): d = 7 needs 4.5x fewer Lanczos steps for 1.4-1.6x more H.v; eigenvalues agree
+// with the plain solver to 1e-12.
+// ---------------------------------------------------------------------------------------------------------
+int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, double tol, int maxit, int kernel,
+               BhSolve* out)
+{
+    const auto t_start = std::chrono::steady_clock::now();
+    int hv_count = 0;
+    LanczosOp plain = [&](const double* x, double* y) {
+        ++hv_count;
+        if (ctx->parent && ctx->parent->hub && ctx->parent->batch_plain) {
+            // lockstep solve: a plain H.v is a filter request of degree 1 with c = 0, e = 1 (s1 = 1, s2 = -0 is skipped)
+            bool handled = false;
+            BH_TRY(bh_batch_filter(ctx, x, y, 0.0, 1.0, cJ, cU, cmu, 1, &handled));
+            if (handled) return (int)BH_OK;
+        }
+        return bh_launch_hv(ctx, cJ, cU, cmu, kernel, x, y);
+    };
+    const int d = ctx->cheb_degree;
+    const bool accel = d > 1 && !ctx->user_matrix && kernel != BH_HV_USER && ctx->D >= 2000 && ncv >= nev + 2 && ncv <= ctx->D;
+    if (!accel) {
+        const int rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
+        out->info.nmatvec = hv_count;
+        return rc;
+    }
+    // Stage 1 has two forms.  Quick (large systems): ONE cycle of `cheb_quick` plain steps gives theta_0 >= E_0 and the
+    // cut is placed by the spectrum-fraction rule alone; stage 2 starts from that cycle's ground Ritz vector.  The wanted
+    // levels must lie below the cut: that is verified on the final Rayleigh-Ritz values, and when it does not hold (the nev
+    // levels span more than cheb_frac of the spectrum: small systems) the solve is repeated with the full form -- cheb_pre
+    // restart cycles of the reference algorithm whose nev-th Ritz value bounds the nev-th level from above (interlacing).
+    // Model (tools/model_block_lanczos.py, m = n = 10): the quick form needs 2-15 % fewer H.v in total and saves ~80 H.v
+    // and ~50 full re-orthogonalisation steps of stage 1 per grid point.
+    const bool quick_ok = ctx->cheb_quick >= 4 && ctx->D >= 50000 && ncv > ctx->cheb_quick + 2;
+    for (int attempt = quick_ok ? 0 : 1; attempt < 2; ++attempt) {
+        const bool quick = attempt == 0;
+        bool retry = false;
+        const int rc = accel_solve(ctx, plain, hv_count, cJ, cU, cmu, nev, ncv, tol, maxit, kernel, quick, &retry, out);
+        if (!retry) {
+            out->info.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+            return rc;
+        }
+    }
+    return bh_fail(ctx, BH_ERR_STATE, "bh_lanczos: unreachable");
 }
 
 int bh_ritz_vector(bh_ctx* ctx, const BhSolve& s, int col, double* x_dev)

@@ -202,3 +202,16 @@ Eigen::SparseMatrix<double> BH::max_bosons_hamiltonian(const std::vector<std::ve
     all.setFromTriplets(trip.begin(), trip.end());
     return all;
 }
+
+void BH::h_MF(double psi, int p, double mu, double J, int q, Eigen::MatrixXd& h)
+{
+    // occupation basis |0> .. |2p>: diagonal -mu k + k (k - 1) / 2 + q J psi^2, hopping to the mean field -q J psi sqrt(k + 1)
+    const int dim = 2 * p + 1;
+    const double c = q * J * psi;
+    for (int k = 0; k < dim; ++k) h(k, k) = -mu * k + 0.5 * k * (k - 1) + c * psi;
+    for (int k = 0; k + 1 < dim; ++k) {
+        const double v = -c * std::sqrt(static_cast<double>(k + 1));
+        h(k + 1, k) = v;
+        h(k, k + 1) = v;
+    }
+}

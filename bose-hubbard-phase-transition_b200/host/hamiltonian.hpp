@@ -31,6 +31,10 @@ Eigen::SparseMatrix<double> fixed_bosons_hamiltonian(const std::vector<std::vect
 Eigen::SparseMatrix<double> max_bosons_hamiltonian(const std::vector<std::vector<int>>& neighbours, int m, int n_min,
                                                    int n_max, double J, double U, double mu);  // :260-288
 
+// single-site mean-field Hamiltonian (:291-310): not on the accelerated path, a small host helper kept so that the
+// reference's own analysis.cpp links against this layer unchanged (INTEGRATION.md option B)
+void h_MF(double psi, int p, double mu, double J, int q, Eigen::MatrixXd& h);
+
 // ---- shim controls (not in the reference) ----
 void set_basis_order(int bh_order);
 void set_device(int device);

@@ -86,6 +86,11 @@ int bh_hamiltonian_csc(bh_ctx* ctx, double cJ, double cU, double cmu, int order,
 /* ---- H.v: replaces Spectra::SparseGenMatProd::perform_op (MatOp/SparseGenMatProd.h:81-86) ---- */
 /* y = (JH*cJ + UH*cU + uH*cmu) x with host vectors in `order` (copies included: this is the MatOp seam). */
 int bh_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, int order, const double* x, double* y);
+/* Page-lock a caller-owned host buffer (cudaHostRegister) so that the copies of bh_hv / bh_eigs / bh_spdm run as direct DMA
+ * at PCIe speed instead of through the driver's pageable staging (2 x 10.8 MB at m = n = 12: ~0.45 ms instead of ~1.8 ms per
+ * bh_hv).  Optional; the caller unregisters before freeing the buffer. */
+int bh_host_register(void* ptr, int64_t bytes);
+int bh_host_unregister(void* ptr);
 /* Same with device vectors in LEX order, launched on the context's stream, no synchronisation. */
 int bh_hv_dev(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x_dev, double* y_dev);
 
