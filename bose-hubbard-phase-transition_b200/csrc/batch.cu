@@ -293,6 +293,7 @@ int bh_batch_filter(bh_ctx* child, const double* x, double* y, double c, double 
     r.x = x; r.y = y; r.c = c; r.e = e; r.cJ = cJ; r.cU = cU; r.cmu = cmu; r.d = d;
     int status = BH_OK;
     *handled = hub->sched.request(me, d, [&](const int* grp, int ng) { return launch_group(parent, hub, grp, ng); }, &status);
+    if (status != BH_OK && !parent->err.empty()) child->err = parent->err;  // the shared launches failed: keep their message
     if (!*handled) hub->single_filters++;
     return status;
 }

@@ -911,18 +911,22 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
     // column block of the re-orthogonalisation: L2-sized blocks for big systems, everything at once when the
     // whole basis is L2-resident anyway (then launch count is what matters)
     const int rblock = ((size_t)ld * 8 * (ncv + 1) <= ((size_t)48 << 20) && !ctx->reorth_block_forced) ? ncv + 1 : ctx->reorth_block;
+    // The opt-in shared-memory limits are properties of the FUNCTIONS (shared by every context and lockstep solve on the
+    // device): they are always raised to the fixed maxima the selection rules below allow, never to a per-call size -- solves
+    // with different ncv run interleaved (lockstep batches; the quick stage 1 uses a shorter basis than stage 2).
     const size_t tiled_smem = sizeof(double) * (size_t)ncv * (CT_ROWS + CT_COLS);
     const bool tiled = tiled_smem <= 200 * 1024 && ctx->compress_tiled;
-    if (tiled) BH_CUDA(ctx, cudaFuncSetAttribute(k_compress_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
+    if (tiled) BH_CUDA(ctx, cudaFuncSetAttribute(k_compress_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const size_t tiled8_smem = sizeof(double) * (size_t)ncv * (CT8_ROWS + CT_COLS);
     const bool tiled8 = tiled && ctx->compress_tiled >= 2 && tiled8_smem <= 110 * 1024;
-    if (tiled8) BH_CUDA(ctx, cudaFuncSetAttribute(k_compress_tiled8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled8_smem));
+    if (tiled8) BH_CUDA(ctx, cudaFuncSetAttribute(k_compress_tiled8, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     const size_t compress_smem = sizeof(double) * ((size_t)ncv * CRsel + (size_t)CK * ncv);
+    if (compress_smem > 227 * 1024) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "restart kernel: ncv too large for shared memory");
     if (compress_smem > 48 * 1024) {
         if (CRsel == 64)
-            BH_CUDA(ctx, cudaFuncSetAttribute(k_compress<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compress_smem));
+            BH_CUDA(ctx, cudaFuncSetAttribute(k_compress<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         else
-            BH_CUDA(ctx, cudaFuncSetAttribute(k_compress<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)compress_smem));
+            BH_CUDA(ctx, cudaFuncSetAttribute(k_compress<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
 
     // cooperative single-launch step: needs every CTA resident and <= COOP_NP row pairs per thread
