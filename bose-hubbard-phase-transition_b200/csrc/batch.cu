@@ -337,6 +337,7 @@ static int ensure_children(bh_ctx* ctx, int nb)
         c->own_stream = false;
         c->fiber = (int)ctx->children.size();
         c->launches = c->h2d_bytes = c->d2h_bytes = 0;
+        c->small_ws = nullptr;
         c->prof_on = false;  // event records live on the parent (BhProfScope)
         c->prof.clear();
         c->prof_free.clear();

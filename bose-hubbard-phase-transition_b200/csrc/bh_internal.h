@@ -159,6 +159,7 @@ struct bh_ctx {
     int coop = 1;          // single cooperative launch per Lanczos step when the residual fits in registers (env BH_COOP)
     int reorth_block = 8;  // basis columns per re-orthogonalisation block (env BH_REORTH_BLOCK)
     bool reorth_block_forced = false;
+    void* small_ws = nullptr;  // bh_small_ws (small.cu): Krylov workspaces of the many-point small-system solver
     // Lanczos workspace (lazy)
     int ws_ncv = 0;
     double* d_V = nullptr;      // (ws_ncv + 1) columns of ld doubles
@@ -224,6 +225,11 @@ int bh_points_lockstep(bh_ctx* ctx, int nb, int64_t npoints, const double* cJ, c
 int bh_batch_filter(bh_ctx* child, const double* x, double* y, double c, double e, double cJ, double cU, double cmu, int d,
                     bool* handled);
 void bh_batch_release(bh_ctx* ctx);
+// many grid points of a small system, one CTA per point (small.cu)
+bool bh_small_supported(const bh_ctx* ctx, int kernel, int64_t npoints, int nb_eigen);
+int bh_points_small(bh_ctx* ctx, int64_t npoints, const double* cJ, const double* cU, const double* cmu, int nb_eigen, double* out3,
+                    bh_eigs_info* infos);
+void bh_small_release(bh_ctx* ctx);
 int bh_build_basis(bh_ctx* ctx);          // K1: states, dU
 int bh_build_hamiltonian(bh_ctx* ctx);    // K2: pattern, J values
 int bh_ensure_orderings(bh_ctx* ctx);     // tags, radix sort, permutations

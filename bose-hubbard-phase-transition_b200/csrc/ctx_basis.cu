@@ -95,6 +95,7 @@ static void free_dev(void* p)
 
 void bh_release_workspace(bh_ctx* ctx)
 {
+    if (!ctx->parent) bh_small_release(ctx);  // lockstep children alias the pointer of their parent
     free_dev(ctx->d_V); ctx->d_V = nullptr;
     free_dev(ctx->d_w); ctx->d_w = nullptr;
     free_dev(ctx->d_f); ctx->d_f = nullptr;

@@ -49,6 +49,38 @@ __device__ __forceinline__ int bh_rank_of(const BhTables& t, uint64_t s)
     return r;
 }
 
+// Off-diagonal part of one row of a nearest-neighbour chain, sum_hops sqrt((n_dst + 1) n_src) x[source], in a single sweep
+// over the sites (see k_hv_free_chain in hv.cu; the caller multiplies by -2J).  x is read with ordinary loads: the callers
+// in small.cu apply H repeatedly inside ONE kernel to vectors that the same CTA wrote a moment ago.
+template <int M, bool CLOSED>
+__device__ __forceinline__ double bh_chain_row_sum(const BhTables& t, uint64_t s, int kk, const double* x)
+{
+    const int n0 = bh_occ(s, 0);
+    int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < M - 1; ++q) {
+        const int nnext = bh_occ(s, q + 1);
+        const int2 gh = t.gh[q][R];  // .x: boson moves q+1 -> q, .y: q -> q+1
+        const double xa = nnext ? x[kk + gh.x] : 0.0;
+        const double xb = nprev ? x[kk + gh.y] : 0.0;
+        acc = fma(t.sq[(nprev + 1) * nnext], xa, acc);
+        acc = fma(t.sq[(nnext + 1) * nprev], xb, acc);
+        tdn += gh.x;
+        tup += gh.y;
+        R -= nnext;
+        nprev = nnext;
+    }
+    if (CLOSED) {
+        const int nl = nprev;  // occupation of the last site
+        const double xa = nl ? x[kk + tdn] : 0.0;  // M-1 -> 0
+        const double xb = n0 ? x[kk + tup] : 0.0;  // 0 -> M-1
+        acc = fma(t.sq[(n0 + 1) * nl], xa, acc);
+        acc = fma(t.sq[(nl + 1) * n0], xb, acc);
+    }
+    return acc;
+}
+
 __device__ __forceinline__ double bh_warp_sum(double v)
 {
 #pragma unroll

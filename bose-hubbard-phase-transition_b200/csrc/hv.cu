@@ -982,7 +982,9 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
             const bool closed = ctx->h_tab.chain == 2;
             // one CTA per 256 rows (not a persistent grid): the exchange kernel on the high-priority communication stream
             // gets its SM slots as soon as the first CTAs retire, so that the two really overlap
-            const int grid = (int)std::max<int64_t>(1, nblocks(nloc, 256));
+            static const int per_sm = getenv("BH_HALO_GRID") ? atoi(getenv("BH_HALO_GRID")) : 0;  // > 0: persistent CTAs per SM
+            const int grid = per_sm > 0 ? (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * per_sm)
+                                        : (int)std::max<int64_t>(1, nblocks(nloc, 256));
             if (nloc > 0 && !(ablate & 2)) {
                 hv_free_fn_t f1 = closed ? hv_chain_part_kernel<true, 1>(ctx->m) : hv_chain_part_kernel<false, 1>(ctx->m);
                 f1<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x - ctx->row0, y, ep);

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <functional>
 #include <limits>
 
@@ -1322,7 +1323,8 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
         return bh_launch_hv(ctx, cJ, cU, cmu, kernel, x, y);
     };
     const int d = ctx->cheb_degree;
-    const bool accel = d > 1 && !ctx->user_matrix && kernel != BH_HV_USER && ctx->D >= 2000 && ncv >= nev + 2 && ncv <= ctx->D;
+    static const int64_t accel_min_d = getenv("BH_ACCEL_MIN_D") ? atoll(getenv("BH_ACCEL_MIN_D")) : 100;  // below: plain mode (r02: raised coverage from D >= 2000, see DESIGN.md "Multiplicities")
+    const bool accel = d > 1 && !ctx->user_matrix && kernel != BH_HV_USER && ctx->D >= accel_min_d && ncv >= nev + 2 && ncv <= ctx->D;
     if (!accel) {
         const int rc = lanczos_core(ctx, plain, false, nev, ncv, tol, maxit, out);
         out->info.nmatvec = hv_count;

@@ -19,8 +19,11 @@ static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); 
 template <int M>
 __global__ void __launch_bounds__(SPDM_THREADS)
 k_spdm(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
-       const double* __restrict__ phi /* full vector, indexed by global LEX rank */, double* __restrict__ part /* [gridDim.x][M][M] */)
+       const double* __restrict__ phi /* full vector, indexed by global LEX rank */, double* __restrict__ part /* [gridDim.x][M][M] */,
+       int64_t phi_stride /* blockIdx.z selects one of several vectors (batched form) */)
 {
+    phi += (int64_t)blockIdx.z * phi_stride;
+    part += (int64_t)blockIdx.z * gridDim.x * M * M;
     __shared__ BhTables t;
     __shared__ double scratch[32];
     bh_stage_tables(&t, gtab);
@@ -63,6 +66,8 @@ k_spdm(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_
 
 __global__ void k_spdm_reduce(int m, int nb, const double* __restrict__ part, double inv_cols, double* __restrict__ rho)
 {
+    part += (int64_t)blockIdx.x * nb * m * m;
+    rho += (int64_t)blockIdx.x * m * m;
     const int i = threadIdx.x % m, j = threadIdx.x / m;
     if (j >= m || i > j) return;
     double t = 0.0;
@@ -72,7 +77,7 @@ __global__ void k_spdm_reduce(int m, int nb, const double* __restrict__ part, do
     rho[j + i * m] = t;
 }
 
-typedef void (*spdm_fn)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double*);
+typedef void (*spdm_fn)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double*, int64_t);
 static spdm_fn spdm_kernel(int m)
 {
     switch (m) {
@@ -121,13 +126,31 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
     dim3 grid(gx, m);
     {
         BhProfScope prof(ctx, BH_PROF_SPDM, 16.0 * (double)nloc * m);  // phi and the packed states, once per source site
-        spdm_kernel(m)<<<grid, SPDM_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, phi_full, d_part);
+        spdm_kernel(m)<<<grid, SPDM_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, phi_full, d_part, 0);
         k_spdm_reduce<<<1, m * m, 0, ctx->stream>>>(m, gx, d_part, 1.0 / (double)ncols, d_rho);
     }
     if (dist) BH_TRY(bh_dist_allreduce_sum(ctx, d_rho, m * m));
     ctx->launches += 2;
     BH_CUDA(ctx, cudaGetLastError());
     BH_D2H(ctx, rho_host, d_rho, sizeof(double) * m * m);
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BH_OK;
+}
+
+// rho of npts vectors phi + p * stride (unpartitioned context) with one launch pair; d_part: npts * 8 * m * m doubles
+int bh_spdm_batch_dev(bh_ctx* ctx, const double* phi, int64_t stride, int npts, int ncols, double* d_part, double* d_rho, double* rho_host)
+{
+    const int m = ctx->m;
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(ctx->nloc, SPDM_THREADS), 8));
+    dim3 grid(gx, m, npts);
+    {
+        BhProfScope prof(ctx, BH_PROF_SPDM, 16.0 * (double)ctx->nloc * m * npts);
+        spdm_kernel(m)<<<grid, SPDM_THREADS, 0, ctx->stream>>>(ctx->d_tab, 0, ctx->nloc, ctx->d_states, phi, d_part, stride);
+        k_spdm_reduce<<<npts, m * m, 0, ctx->stream>>>(m, gx, d_part, 1.0 / (double)ncols, d_rho);
+    }
+    ctx->launches += 2;
+    BH_CUDA(ctx, cudaGetLastError());
+    BH_D2H(ctx, rho_host, d_rho, sizeof(double) * (size_t)npts * m * m);
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BH_OK;
 }
@@ -217,6 +240,8 @@ extern "C" int bh_points(bh_ctx* ctx, const double* cJ, const double* cU, const 
                          int kernel, double* out3, bh_eigs_info* infos)
 {
     if (!ctx || !cJ || !cU || !cmu || !out3 || npoints < 0) return bh_fail(ctx, BH_ERR_ARG, "bh_points: bad argument");
+    // many points of a small system (small.cu): one CTA per grid point, a whole restart cycle per launch
+    if (ctx->D && bh_small_supported(ctx, kernel, npoints, nb_eigen)) return bh_points_small(ctx, npoints, cJ, cU, cmu, nb_eigen, out3, infos);
     // lockstep batching (batch.cu): ctx->batch solves run together and share their H.v launches; same results point by point
     if (ctx->batch >= 2 && npoints >= 2 && ctx->D && nb_eigen >= 3 && bh_batch_supported(ctx, kernel))
         return bh_points_lockstep(ctx, (int)std::min<int64_t>(ctx->batch, npoints), npoints, cJ, cU, cmu, nb_eigen, kernel, out3, infos);

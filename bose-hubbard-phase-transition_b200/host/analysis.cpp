@@ -147,12 +147,16 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
         auto worker = [&](int d) {
             try {
                 const int B = std::max(1, std::min(4, opt.batch));
+                int64_t dim = 0;
+                bh_dimension(m, n, &dim);
+                // a chunk of tasks per call: bh_points keeps B solves in lockstep (shared H.v launches, same results) and
+                // refills a finished solve from the chunk; small systems (D <= 100 000) are solved one CTA per grid point,
+                // so they are handed over in chunks large enough to fill the SMs of the GPU
+                const int chunk = B > 1 ? ((dim <= 100000 && kernel == BH_HV_MATRIX_FREE) ? 160 : std::min(16, 4 * B)) : 1;
+                std::vector<int> ts(chunk);
+                std::vector<double> cJ(chunk), cU(chunk), cmu(chunk), p1s(chunk), out3(3 * (size_t)chunk);
                 for (;;) {
-                    // a chunk of tasks per call: bh_points keeps B solves in lockstep (shared H.v launches, same results) and
-                    // refills a finished solve from the chunk
-                    const int chunk = B > 1 ? std::min(16, 4 * B) : 1;
-                    int ts[16], nt = 0;
-                    double cJ[16], cU[16], cmu[16], p1s[16], out3[48];
+                    int nt = 0;
                     while (nt < chunk) {
                         const int t = next.fetch_add(1);
                         if (t >= ntasks) break;
@@ -173,15 +177,15 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
                         ts[nt++] = t;
                     }
                     if (nt == 0) break;
-                    const int rc = nt == 1 ? bh_point(ctxs[d], cJ[0], cU[0], cmu[0], nb_eigen, kernel, out3, nullptr, nullptr, nullptr)
-                                           : bh_points(ctxs[d], cJ, cU, cmu, nt, nb_eigen, kernel, out3, nullptr);
+                    const int rc = nt == 1 ? bh_point(ctxs[d], cJ[0], cU[0], cmu[0], nb_eigen, kernel, out3.data(), nullptr, nullptr, nullptr)
+                                           : bh_points(ctxs[d], cJ.data(), cU.data(), cmu.data(), nt, nb_eigen, kernel, out3.data(), nullptr);
                     if (rc == BH_ERR_ARG) throw std::invalid_argument(bh_last_error(ctxs[d]));
                     if (rc != BH_OK) throw std::runtime_error(bh_last_error(ctxs[d]));
                     std::lock_guard<std::mutex> lk(mtx);
                     for (int q = 0; q < nt; ++q) {
                         const int t = ts[q];
                         const int i = shift_rows ? t : t / g.num2, j = shift_rows ? 0 : t % g.num2;
-                        const double* o3 = out3 + 3 * q;
+                        const double* o3 = out3.data() + 3 * q;
                         for (int jj = j; jj < (shift_rows ? g.num2 : j + 1); ++jj) {
                             const int index = i * g.num1 + jj;  // src/analysis.cpp:341 (sic)
                             if (index >= 0 && index < total) {
