@@ -189,7 +189,7 @@ static batch_fn batch_kernel(int m, int nb, bool src_il)
 bool bh_batch_supported(const bh_ctx* ctx, int kernel)
 {
     return kernel == BH_HV_MATRIX_FREE && !ctx->user_matrix && !ctx->partitioned && ctx->h_tab.chain == 2 && ctx->m >= 6 &&
-           ctx->m <= 16 && ctx->cheb_degree > 1 && ctx->free_variant == 1 && !ctx->parent;
+           ctx->m <= 16 && ctx->cheb_degree > 1 && !ctx->parent;
 }
 
 // The Chebyshev filters of the parked fibers fib[0..nb), nb in {2, 4}, applied together (see bh_lanczos, stage 2).
@@ -333,7 +333,6 @@ static int ensure_children(bh_ctx* ctx, int nb)
         c->parent = ctx;
         c->children.clear();
         c->hub = nullptr;
-        c->split = nullptr;
         c->own_stream = false;
         c->fiber = (int)ctx->children.size();
         c->launches = c->h2d_bytes = c->d2h_bytes = 0;

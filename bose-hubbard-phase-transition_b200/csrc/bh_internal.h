@@ -93,24 +93,9 @@ struct bh_ctx {
     BhTables h_tab;
     BhTables* d_tab = nullptr;
     int max_row = 0;  // max entries per row of H (incl. diagonal)
-    // matrix-free H.v (env BH_FREE_VARIANT): 0 = fully unrolled site pairs, 1 = chain sweep / bond list per row,
-    // 2 = split (prefix x suffix) kernel for chains on an unpartitioned context (hv_split.cu), else as 1
-    int free_variant = 1;
-    void* split = nullptr;  // bh_split_state (hv_split.cu), built on first use
-    int split_G = 4;        // prefixes per warp (env BH_SPLIT_G)
-    int split_UJ = 2;       // hops in flight together per prefix (env BH_SPLIT_UJ)
-    int split_nx = 8;       // warps of a CTA along the suffix direction (env BH_SPLIT_NX: 1, 2, 4, 8)
-    int split_p = 0;        // prefix sites, 0 = m / 2 (env BH_SPLIT_P)
-    int hv_variant = 2;  // stored H.v: 0 = CSR-stream, 1 = TMA-staged CSR-stream, 2 = SELL-32 (default; env BH_HV_VARIANT)
-    int hv_stages = 3;   // ring depth of the TMA variant (env BH_HV_STAGES)
-    int tile_cap = 0;    // entries per shared-memory stage of the TMA variant
-    size_t hv_smem_configured = 0;
-    // SELL-32 copy of the stored H (variant 2): slices of 32 consecutive rows, column-major inside a slice,
+    // SELL-32 copy of the stored H: slices of 32 consecutive rows, column-major inside a slice,
     // padded to the longest row of the slice (padding = zero value pointing at the row's own column)
     int64_t sell_nslices = 0, sell_entries = 0;
-    double hybrid_frac = 0.35;      // BH_HV_HYBRID: fraction of the rows taken from the stored slices (env BH_HYBRID_FRAC)
-    int hybrid_sell_blocks = 3;     // ... and SELL-role CTAs out of every 8 (env BH_HYBRID_BLOCKS)
-    int64_t hyb_split = -1, hyb_slices = 0, hyb_entries = 0;
     int sell_sigma = 256;           // sorting window (rows), multiple of 32 (env BH_SELL_SIGMA; 32 = plain SELL-32)
     int* d_sell_row = nullptr;      // [nslices * 32] slot -> row (-1 = padding slot)
     int* d_sell_ptr = nullptr;      // [nslices + 1] entry offset of each slice
@@ -149,12 +134,6 @@ struct bh_ctx {
     int hv_block_cols = 0;
     double* d_gram_part = nullptr;   // per-CTA partial Gram matrices
     int compress_tiled = 2;  // restart GEMM (env BH_COMPRESS_TILED): 0 shared-memory rows, 1 4x4 register tiles, 2 4x8 register tiles
-    int coop_ch = 8;       // basis columns per block of the cooperative step's block Gram-Schmidt (env BH_COOP_CH: 4 or 8)
-    // EXPERIMENT, rejected: skip the update sweep of a block whose coefficients are all < tau * beta.
-    // +8 % points/s at tau = 1e-13, but tau = 1e-12 breaks the 1e-10 parity at m=n=12 and 1e-14 the J = 0 recovery; keep 0.
-    double reorth_tau = 0.0;  // env BH_REORTH_TAU
-    int coop_smem = 0;      // cooperative step with the residual in shared memory, 3 CTAs per SM (env BH_COOP_SMEM)
-    int coop_prefetch = 0;  // fused cooperative step: row chunks of the next block prefetched into L2 before each grid barrier (env BH_COOP_PREFETCH; measured slower: 2 -> -1 %, 10 -> -6 %)
     int coop_fused = 1;    // cooperative step: update with block k fused with the dot products of block k+1 (env BH_COOP_FUSED)
     int coop = 1;          // single cooperative launch per Lanczos step when the residual fits in registers (env BH_COOP)
     int reorth_block = 8;  // basis columns per re-orthogonalisation block (env BH_REORTH_BLOCK)
@@ -242,10 +221,6 @@ struct BhEpilogue {
 };
 int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel, const double* x_dev, double* y_dev,
                  const BhEpilogue& ep = BhEpilogue());
-// split matrix-free kernel for chains (hv_split.cu)
-bool bh_split_supported(const bh_ctx* ctx);
-int bh_launch_hv_split(bh_ctx* ctx, double cJ, double cU, double cmu, const double* x_dev, double* y_dev, const BhEpilogue& ep);
-void bh_split_release(bh_ctx* ctx);
 // rigorous (Gershgorin) bounds of the spectrum of H(cJ, cU, cmu); model contexts only
 int bh_spectrum_bounds(bh_ctx* ctx, double cJ, double cU, double cmu, double* lo, double* hi);
 int bh_dist_allreduce_max(bh_ctx* ctx, double* buf_dev, int64_t count);

@@ -58,24 +58,12 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
         return bh_fail(nullptr, BH_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     ctx->own_stream = true;
-    if (const char* v = getenv("BH_HV_VARIANT")) ctx->hv_variant = atoi(v);
-    if (const char* v = getenv("BH_FREE_VARIANT")) ctx->free_variant = atoi(v);
     if (const char* v = getenv("BH_BATCH")) ctx->batch = std::min(4, std::max(1, atoi(v)));
     if (const char* v = getenv("BH_BATCH_PLAIN")) ctx->batch_plain = atoi(v);
-    if (const char* v = getenv("BH_SPLIT_G")) ctx->split_G = atoi(v);
-    if (const char* v = getenv("BH_SPLIT_P")) ctx->split_p = atoi(v);
-    if (const char* v = getenv("BH_SPLIT_UJ")) ctx->split_UJ = atoi(v);
-    if (const char* v = getenv("BH_SPLIT_NX")) ctx->split_nx = atoi(v);
-    if (const char* v = getenv("BH_HYBRID_FRAC")) ctx->hybrid_frac = std::min(1.0, std::max(0.0, atof(v)));
-    if (const char* v = getenv("BH_HYBRID_BLOCKS")) ctx->hybrid_sell_blocks = std::min(7, std::max(1, atoi(v)));
     if (const char* v = getenv("BH_SELL_SIGMA")) ctx->sell_sigma = std::min(1024, std::max(32, atoi(v) / 32 * 32));
     if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
     if (const char* v = getenv("BH_COOP_FUSED")) ctx->coop_fused = atoi(v);
     if (const char* v = getenv("BH_RR_GRAM")) ctx->rr_gram = atoi(v);
-    if (const char* v = getenv("BH_COOP_SMEM")) ctx->coop_smem = atoi(v);
-    if (const char* v = getenv("BH_COOP_PREFETCH")) ctx->coop_prefetch = std::max(0, std::min(10, atoi(v)));
-    if (const char* v = getenv("BH_REORTH_TAU")) ctx->reorth_tau = atof(v);
-    if (const char* v = getenv("BH_COOP_CH")) ctx->coop_ch = (atoi(v) == 4) ? 4 : 8;
     if (const char* v = getenv("BH_COMPRESS_TILED")) ctx->compress_tiled = atoi(v);
     if (const char* v = getenv("BH_CHEB_DEGREE")) ctx->cheb_degree = std::max(1, atoi(v));
     if (const char* v = getenv("BH_CHEB_PRE")) ctx->cheb_pre = std::max(1, atoi(v));
@@ -122,7 +110,6 @@ int bh_release_system(bh_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     bh_batch_release(ctx);  // lockstep children alias the arrays freed below
-    bh_split_release(ctx);
     free_dev(ctx->d_tab); ctx->d_tab = nullptr;
     free_dev(ctx->d_states); ctx->d_states = nullptr;
     free_dev(ctx->d_dU); ctx->d_dU = nullptr;
@@ -140,7 +127,6 @@ int bh_release_system(bh_ctx* ctx)
     ctx->sell_valid = ctx->sell_partial_valid = false;
     ctx->sell_cJ = ctx->sell_cU = ctx->sell_cmu = 0.0;
     ctx->sell_nslices = ctx->sell_entries = 0;
-    ctx->hyb_split = -1;
     free_dev(ctx->d_tags); ctx->d_tags = nullptr;
     free_dev(ctx->d_perm_tag); ctx->d_perm_tag = nullptr;
     free_dev(ctx->d_inv_tag); ctx->d_inv_tag = nullptr;

@@ -4,11 +4,10 @@
 // (reference external/spectra/include/Spectra/MatOp/SparseGenMatProd.h:81-86,
 //  include/Eigen/src/SparseCore/SparseDenseProduct.h:86-107).
 //
-// K3  streams the CSR arrays of the materialised H once per product, fully coalesced: a warp owns 32
-//     consecutive rows, its lanes stride over the contiguous entry range of those rows (one coalesced
-//     128 B / 256 B request per warp instruction for col / val), gather x through L2, park the products
-//     in shared memory and then each lane adds up its own row in column order (deterministic, the same
-//     summation order as the reference's column-ordered scatter).  Algorithmic bytes: 12*nnz + 4*(D+1) + 16*D.
+// K3  streams a SELL-32-sigma copy of the materialised H once per product: a warp owns a slice of 32 rows, lane = row,
+//     column-major entries (perfectly coalesced index / value loads), each lane sums its row in column order
+//     (deterministic).  Algorithmic bytes: 12*nnz + 4*(D+1) + 16*D.  (The CSR-stream, TMA-ring, unrolled, hybrid and
+//     split variants of round 1 were measured slower and removed in round 2: DESIGN.md section 10, git history.)
 // K4  stores no matrix: thread k re-derives row k from the packed state (8 B) with the O(1) incremental
 //     rank, so the HBM traffic is x, y, the packed states and the U-diagonal only.
 #include <algorithm>
@@ -21,182 +20,6 @@ static inline int nblocks(int64_t n, int bs) { return (int)((n + bs - 1) / bs); 
 // ---------------------------------------------------------------------------------------------
 // K3
 // ---------------------------------------------------------------------------------------------
-#define HV_WARPS 8
-
-__global__ void __launch_bounds__(HV_WARPS * 32)
-k_hv_csr(int64_t D, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-         const double* __restrict__ x, double* __restrict__ y, int max_row)
-{
-    extern __shared__ double sprod[];
-    const int lane = threadIdx.x & 31;
-    double* prod = sprod + (size_t)(threadIdx.x >> 5) * 32 * max_row;
-    const int64_t ntiles = (D + 31) >> 5;
-    const int64_t wstride = (int64_t)gridDim.x * HV_WARPS;
-    for (int64_t tile = (int64_t)blockIdx.x * HV_WARPS + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
-        const int64_t r = (tile << 5) + lane;
-        int a = 0, b = 0;
-        if (r < D) {
-            a = __ldg(rowptr + r);
-            b = __ldg(rowptr + r + 1);
-        }
-        const int e0 = __shfl_sync(0xffffffffu, a, 0);
-        const int nvalid = (int)min((int64_t)32, D - (tile << 5));
-        const int e1 = __shfl_sync(0xffffffffu, b, nvalid - 1);
-        // phase 1: products, entry-parallel and coalesced; 4 independent requests in flight per lane
-        int e = e0 + lane;
-        for (; e + 96 < e1; e += 128) {
-            const int c0 = __ldg(col + e), c1 = __ldg(col + e + 32), c2 = __ldg(col + e + 64), c3 = __ldg(col + e + 96);
-            const double v0 = __ldg(val + e), v1 = __ldg(val + e + 32), v2 = __ldg(val + e + 64), v3 = __ldg(val + e + 96);
-            const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-            prod[e - e0] = v0 * x0;
-            prod[e - e0 + 32] = v1 * x1;
-            prod[e - e0 + 64] = v2 * x2;
-            prod[e - e0 + 96] = v3 * x3;
-        }
-        for (; e < e1; e += 32) prod[e - e0] = __ldg(val + e) * __ldg(x + __ldg(col + e));
-        __syncwarp();
-        // phase 2: every lane sums its own row in column order
-        if (r < D) {
-            double acc = 0.0;
-            for (int q = a - e0; q < b - e0; ++q) acc += prod[q];
-            y[r] = acc;
-        }
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3, TMA-staged variant: every warp runs its own ring of STAGES shared-memory stages.  Lane 0 issues three
-// bulk async copies (cp.async.bulk -> UBLKCP) per 32-row tile -- the row-pointer slice, the column indices and
-// the values of the tile's contiguous entry range -- completing on an mbarrier, so the matrix stream is
-// prefetched STAGES-1 tiles ahead of the arithmetic and needs no registers.  The matrix is read exactly
-// once and marked evict-first in L2 so that it does not displace x (which the gathers re-use).
-// ---------------------------------------------------------------------------------------------
-#define HVT_WARPS 4
-#define HVT_BATCH 8
-#define HVT_RP 36  // row-pointer entries copied per tile (33 needed, 16-byte multiple)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-
-template <int STAGES>
-__global__ void __launch_bounds__(HVT_WARPS * 32)
-k_hv_csr_tma(int64_t D, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-             const double* __restrict__ x, double* __restrict__ y, int tile_cap)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t stage_bytes = (size_t)tile_cap * 12 + HVT_RP * 4;
-    unsigned char* wbase = smem_raw + (size_t)warp * STAGES * stage_bytes;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)HVT_WARPS * STAGES * stage_bytes) + warp * STAGES;
-    const int64_t ntiles = (D + 31) >> 5;
-    const int64_t wstride = (int64_t)gridDim.x * HVT_WARPS;
-    const int64_t wfirst = (int64_t)blockIdx.x * HVT_WARPS + warp;
-    uint64_t policy = 0;
-    if (lane == 0) {
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-        for (int s = 0; s < STAGES; ++s) mbar_init(mbar + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    auto issue = [&](int64_t tile, int stage) {  // lane 0 only
-        const int64_t r0 = tile << 5;
-        const int64_t r1 = min(r0 + 32, D);
-        const int e0 = __ldg(rowptr + r0), e1 = __ldg(rowptr + r1);
-        const int a0 = e0 & ~3, a1 = (e1 + 3) & ~3;
-        const uint32_t n = (uint32_t)(a1 - a0);
-        unsigned char* sb = wbase + (size_t)stage * stage_bytes;
-        mbar_expect_tx(mbar + stage, n * 12u + HVT_RP * 4u);
-        tma_load_1d(sb, val + a0, n * 8u, mbar + stage, policy);
-        tma_load_1d(sb + (size_t)tile_cap * 8, col + a0, n * 4u, mbar + stage, policy);
-        tma_load_1d(sb + (size_t)tile_cap * 12, rowptr + r0, HVT_RP * 4u, mbar + stage, policy);
-    };
-
-    if (lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            const int64_t t = wfirst + (int64_t)s * wstride;
-            if (t < ntiles) issue(t, s);
-        }
-    }
-    int k = 0;
-    for (int64_t tile = wfirst; tile < ntiles; tile += wstride, ++k) {
-        const int stage = k % STAGES;
-        mbar_wait(mbar + stage, (uint32_t)((k / STAGES) & 1));
-        unsigned char* sb = wbase + (size_t)stage * stage_bytes;
-        double* sval = reinterpret_cast<double*>(sb);
-        const int* scol = reinterpret_cast<const int*>(sb + (size_t)tile_cap * 8);
-        const int* srp = reinterpret_cast<const int*>(sb + (size_t)tile_cap * 12);
-        const int nvalid = (int)min((int64_t)32, D - (tile << 5));
-        const int e0 = srp[0], e1 = srp[nvalid];
-        const int a0 = e0 & ~3;
-        // phase 1: products in place of the values (entry-parallel, conflict-free shared accesses)
-        // (gathers issued in batches of HVT_BATCH per lane so that their L2 latency overlaps)
-        const int nE = e1 - a0;
-        for (int base = e0 - a0 + lane; base < nE; base += 32 * HVT_BATCH) {
-            int c[HVT_BATCH];
-            double xv[HVT_BATCH];
-#pragma unroll
-            for (int u = 0; u < HVT_BATCH; ++u) c[u] = (base + 32 * u < nE) ? scol[base + 32 * u] : -1;
-#pragma unroll
-            for (int u = 0; u < HVT_BATCH; ++u) xv[u] = (c[u] >= 0) ? __ldg(x + c[u]) : 0.0;
-#pragma unroll
-            for (int u = 0; u < HVT_BATCH; ++u)
-                if (c[u] >= 0) sval[base + 32 * u] *= xv[u];
-        }
-        __syncwarp();
-        // phase 2: each lane adds up its own row in column order
-        if (lane < nvalid) {
-            double acc = 0.0;
-            for (int q = srp[lane] - a0; q < srp[lane + 1] - a0; ++q) acc += sval[q];
-            y[(tile << 5) + lane] = acc;
-        }
-        // the stage is rewritten by the async proxy next: order our generic-proxy accesses before it
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-            const int64_t nt = tile + (int64_t)STAGES * wstride;
-            if (nt < ntiles) issue(nt, stage);
-        }
-    }
-}
-
-// max over 32-row tiles of the (16-byte aligned) entry count -> stage capacity of the TMA variant
-__global__ void k_tile_cap(int64_t D, const int* __restrict__ rowptr, int* __restrict__ out)
-{
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t r0 = t << 5;
-    if (r0 >= D) return;
-    const int64_t r1 = min(r0 + 32, D);
-    const int a0 = rowptr[r0] & ~3, a1 = (rowptr[r1] + 3) & ~3;
-    atomicMax(out, a1 - a0);
-}
-
 // ---------------------------------------------------------------------------------------------
 // K3, SELL-32 variant: one warp per slice of 32 rows, lane = row, entries column-major inside the slice.
 // Index / value loads are perfectly coalesced streaming loads (evict-first), no shared memory, full
@@ -245,39 +68,6 @@ k_hv_sell(int64_t D, int64_t nslices, const int* __restrict__ sptr, const int* _
 // ---------------------------------------------------------------------------------------------
 // K4
 // ---------------------------------------------------------------------------------------------
-template <int M>
-__global__ void __launch_bounds__(256)
-k_hv_free(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
-          const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
-          double* __restrict__ y)
-{
-    __shared__ BhTables t;
-    bh_stage_tables(&t, gtab);
-    const double shift = __dmul_rn(-(double)t.n, cmu);
-    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k = row0 + l;  // global LEX rank; states / dU / y are local, x is the full vector
-        const uint64_t s = states[l];
-        int dn[M], up[M];
-        bh_rank_prefix<M>(t, s, dn, up);
-        double acc = 0.0;
-#pragma unroll
-        for (int src = 0; src < M; ++src) {
-            const int ns = bh_occ(s, src);
-            if (ns == 0) continue;
-#pragma unroll
-            for (int dst = 0; dst < M; ++dst) {
-                if (dst == src) continue;
-                const int w = t.w[dst][src];  // block-uniform
-                if (w == 0) continue;
-                const int tgt = (int)k + (dst < src ? dn[src] - dn[dst] : up[dst] - up[src]);
-                acc += (double)w * t.sq[(bh_occ(s, dst) + 1) * ns] * __ldg(x + tgt);
-            }
-        }
-        const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
-        y[l] = diag * x[k] - cJ * acc;
-    }
-}
-
 typedef void (*hv_free_fn_t)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double, double, double,
                              const double*, double*, BhEpilogue);
 
@@ -383,11 +173,11 @@ k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, cons
 }
 
 // Row-partitioned form of the chain kernel (one large eigensolve over several GPUs, BASELINE.json config 5): the hops of a
-// row are split by where their source element lives.  PHASE 1 takes the hops whose source is in this rank's own slice
+// row are split by where their source element lives.  This kernel takes the hops whose source is in this rank's own slice
 // [row0, row0 + D) -- x is then the LOCAL slice, addressed through a pointer shifted by -row0 -- plus the diagonal and the
-// epilogue, and runs while the halo exchange is in flight; PHASE 2 adds the hops whose source lies in another rank's slice
-// from the exchanged full-length buffer.  Both are the single sweep of k_hv_free_chain with a range test per hop.
-template <int M, bool CLOSED, int PHASE>
+// epilogue, and runs while the halo exchange is in flight: the single sweep of k_hv_free_chain with a range test per hop.
+// The hops whose source lies in another rank's slice are a stored CSR matrix applied afterwards (k_hv_remote).
+template <int M, bool CLOSED>
 __global__ void __launch_bounds__(256, CHAIN_MIN_BLOCKS)
 k_hv_free_chain_part(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
                      const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
@@ -406,7 +196,7 @@ k_hv_free_chain_part(const BhTables* __restrict__ gtab, int64_t row0, int64_t D,
         double acc = 0.0;
         auto hop = [&](int cond, int tgt, double amp) {
             const bool local = ((unsigned)tgt - lo) < len;
-            const bool take = cond && (PHASE == 1 ? local : !local);
+            const bool take = cond && local;
             const double xv = take ? __ldg(x + tgt) : 0.0;
             acc = fma(amp, xv, acc);
         };
@@ -426,16 +216,12 @@ k_hv_free_chain_part(const BhTables* __restrict__ gtab, int64_t row0, int64_t D,
             hop(nl, kk + tdn, t.sq[(n0 + 1) * nl]);
             hop(n0, kk + tup, t.sq[(nl + 1) * n0]);
         }
-        if (PHASE == 1) {
-            const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
-            const double xv = x[k];
-            double out = ep.s1 * (diag * xv - (2.0 * cJ) * acc);
-            if (ep.s2 != 0.0) out = fma(ep.s2, xv, out);
-            if (ep.z) out = fma(ep.s3, ep.z[l], out);
-            y[l] = out;
-        } else if (acc != 0.0) {
-            y[l] = fma(ep.s1 * (-2.0 * cJ), acc, y[l]);
-        }
+        const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
+        const double xv = x[k];
+        double out = ep.s1 * (diag * xv - (2.0 * cJ) * acc);
+        if (ep.s2 != 0.0) out = fma(ep.s2, xv, out);
+        if (ep.z) out = fma(ep.s3, ep.z[l], out);
+        y[l] = out;
     }
 }
 
@@ -499,132 +285,24 @@ static hv_free_fn_t hv_chain_kernel(int m)
 }
 
 
-// K3 + K4 hybrid for chains: rows [0, split) are taken from the stored SELL slices (HBM-bound: ~29 % of the issue slots at
-// full bandwidth), rows [split, D) are re-derived matrix-free (issue-bound, almost no HBM traffic), by different CTAs
-// of ONE launch, interleaved so that every SM runs both roles: the memory system and the issue slots are busy together.
-template <int M, bool CLOSED>
-__global__ void __launch_bounds__(256, 4)
-k_hv_hybrid(const BhTables* __restrict__ gtab, int64_t D, int64_t split, int64_t nsl, int ks, const int* __restrict__ sptr,
-            const int* __restrict__ srow, const int* __restrict__ scol, const double* __restrict__ sval,
-            const uint64_t* __restrict__ states, const double* __restrict__ dU, double cJ, double cU, double cmu,
-            const double* __restrict__ x, double* __restrict__ y, BhEpilogue ep)
-{
-    const int period = 8;
-    const int grp = blockIdx.x / period, pos = blockIdx.x % period, ngrp = gridDim.x / period;
-    if (pos < ks) {
-        // ---- stored role ----
-        const int lane = threadIdx.x & 31;
-        const int64_t nw = (int64_t)ngrp * ks * (blockDim.x >> 5);
-        for (int64_t s = ((int64_t)grp * ks + pos) * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nsl; s += nw) {
-            const int base = __ldg(sptr + s), end = __ldg(sptr + s + 1);
-            double acc = 0.0;
-            for (int p = base + lane; p < end; p += 32 * SELL_BATCH) {
-                int c[SELL_BATCH];
-                double v[SELL_BATCH], xv[SELL_BATCH];
-#pragma unroll
-                for (int u = 0; u < SELL_BATCH; ++u) {
-                    const bool ok = p + 32 * u < end;
-                    c[u] = ok ? __ldcs(scol + p + 32 * u) : -1;
-                    v[u] = ok ? __ldcs(sval + p + 32 * u) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < SELL_BATCH; ++u) xv[u] = (c[u] >= 0) ? __ldg(x + c[u]) : 0.0;
-#pragma unroll
-                for (int u = 0; u < SELL_BATCH; ++u) acc = fma(v[u], xv[u], acc);
-            }
-            const int r = __ldg(srow + (s << 5) + lane);
-            if (r >= 0) {
-                double out = ep.s1 * acc;
-                if (ep.s2 != 0.0) out = fma(ep.s2, x[r], out);
-                if (ep.z) out = fma(ep.s3, ep.z[r], out);
-                y[r] = out;
-            }
-        }
-        return;
-    }
-    // ---- matrix-free role ----
-    __shared__ BhTables t;
-    bh_stage_tables(&t, gtab);
-    const double shift = __dmul_rn(-(double)t.n, cmu);
-    const int kc = period - ks;
-    const int64_t nthreads = (int64_t)ngrp * kc * blockDim.x;
-    for (int64_t k = split + ((int64_t)grp * kc + (pos - ks)) * blockDim.x + threadIdx.x; k < D; k += nthreads) {
-        const uint64_t s = states[k];
-        const int kk = (int)k;
-        const int n0 = bh_occ(s, 0);
-        int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
-        double acc = 0.0;
-#pragma unroll
-        for (int q = 0; q < M - 1; ++q) {
-            const int nnext = bh_occ(s, q + 1);
-            const int2 gh = t.gh[q][R];
-            const double xa = nnext ? __ldg(x + (kk + gh.x)) : 0.0;
-            const double xb = nprev ? __ldg(x + (kk + gh.y)) : 0.0;
-            acc = fma(t.sq[(nprev + 1) * nnext], xa, acc);
-            acc = fma(t.sq[(nnext + 1) * nprev], xb, acc);
-            tdn += gh.x;
-            tup += gh.y;
-            R -= nnext;
-            nprev = nnext;
-        }
-        if (CLOSED) {
-            const int nl = nprev;
-            const double xa = nl ? __ldg(x + (kk + tdn)) : 0.0;
-            const double xb = n0 ? __ldg(x + (kk + tup)) : 0.0;
-            acc = fma(t.sq[(n0 + 1) * nl], xa, acc);
-            acc = fma(t.sq[(nl + 1) * n0], xb, acc);
-        }
-        const double diag = __dadd_rn(__dmul_rn(dU[k], cU), shift);
-        const double xv = x[k];
-        double out = ep.s1 * (diag * xv - (2.0 * cJ) * acc);
-        if (ep.s2 != 0.0) out = fma(ep.s2, xv, out);
-        if (ep.z) out = fma(ep.s3, ep.z[k], out);
-        y[k] = out;
-    }
-}
-
-typedef void (*hv_hybrid_fn_t)(const BhTables*, int64_t, int64_t, int64_t, int, const int*, const int*, const int*, const double*,
-                               const uint64_t*, const double*, double, double, double, const double*, double*, BhEpilogue);
 template <bool CLOSED>
-static hv_hybrid_fn_t hv_hybrid_kernel(int m)
-{
-    switch (m) {
-        case 3: return k_hv_hybrid<3, CLOSED>;
-        case 4: return k_hv_hybrid<4, CLOSED>;
-        case 5: return k_hv_hybrid<5, CLOSED>;
-        case 6: return k_hv_hybrid<6, CLOSED>;
-        case 7: return k_hv_hybrid<7, CLOSED>;
-        case 8: return k_hv_hybrid<8, CLOSED>;
-        case 9: return k_hv_hybrid<9, CLOSED>;
-        case 10: return k_hv_hybrid<10, CLOSED>;
-        case 11: return k_hv_hybrid<11, CLOSED>;
-        case 12: return k_hv_hybrid<12, CLOSED>;
-        case 13: return k_hv_hybrid<13, CLOSED>;
-        case 14: return k_hv_hybrid<14, CLOSED>;
-        case 15: return k_hv_hybrid<15, CLOSED>;
-        case 16: return k_hv_hybrid<16, CLOSED>;
-    }
-    return nullptr;
-}
-
-template <bool CLOSED, int PHASE>
 static hv_free_fn_t hv_chain_part_kernel(int m)
 {
     switch (m) {
-        case 3: return k_hv_free_chain_part<3, CLOSED, PHASE>;
-        case 4: return k_hv_free_chain_part<4, CLOSED, PHASE>;
-        case 5: return k_hv_free_chain_part<5, CLOSED, PHASE>;
-        case 6: return k_hv_free_chain_part<6, CLOSED, PHASE>;
-        case 7: return k_hv_free_chain_part<7, CLOSED, PHASE>;
-        case 8: return k_hv_free_chain_part<8, CLOSED, PHASE>;
-        case 9: return k_hv_free_chain_part<9, CLOSED, PHASE>;
-        case 10: return k_hv_free_chain_part<10, CLOSED, PHASE>;
-        case 11: return k_hv_free_chain_part<11, CLOSED, PHASE>;
-        case 12: return k_hv_free_chain_part<12, CLOSED, PHASE>;
-        case 13: return k_hv_free_chain_part<13, CLOSED, PHASE>;
-        case 14: return k_hv_free_chain_part<14, CLOSED, PHASE>;
-        case 15: return k_hv_free_chain_part<15, CLOSED, PHASE>;
-        case 16: return k_hv_free_chain_part<16, CLOSED, PHASE>;
+        case 3: return k_hv_free_chain_part<3, CLOSED>;
+        case 4: return k_hv_free_chain_part<4, CLOSED>;
+        case 5: return k_hv_free_chain_part<5, CLOSED>;
+        case 6: return k_hv_free_chain_part<6, CLOSED>;
+        case 7: return k_hv_free_chain_part<7, CLOSED>;
+        case 8: return k_hv_free_chain_part<8, CLOSED>;
+        case 9: return k_hv_free_chain_part<9, CLOSED>;
+        case 10: return k_hv_free_chain_part<10, CLOSED>;
+        case 11: return k_hv_free_chain_part<11, CLOSED>;
+        case 12: return k_hv_free_chain_part<12, CLOSED>;
+        case 13: return k_hv_free_chain_part<13, CLOSED>;
+        case 14: return k_hv_free_chain_part<14, CLOSED>;
+        case 15: return k_hv_free_chain_part<15, CLOSED>;
+        case 16: return k_hv_free_chain_part<16, CLOSED>;
     }
     return nullptr;
 }
@@ -778,32 +456,6 @@ int bh_mark_halo_chunks(bh_ctx* ctx, unsigned char* flags_dev)
     return BH_OK;
 }
 
-typedef void (*hv_free_fn)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double, double, double,
-                           const double*, double*);
-
-static hv_free_fn hv_free_kernel(int m)
-{
-    switch (m) {
-        case 1: return k_hv_free<1>;
-        case 2: return k_hv_free<2>;
-        case 3: return k_hv_free<3>;
-        case 4: return k_hv_free<4>;
-        case 5: return k_hv_free<5>;
-        case 6: return k_hv_free<6>;
-        case 7: return k_hv_free<7>;
-        case 8: return k_hv_free<8>;
-        case 9: return k_hv_free<9>;
-        case 10: return k_hv_free<10>;
-        case 11: return k_hv_free<11>;
-        case 12: return k_hv_free<12>;
-        case 13: return k_hv_free<13>;
-        case 14: return k_hv_free<14>;
-        case 15: return k_hv_free<15>;
-        case 16: return k_hv_free<16>;
-    }
-    return nullptr;
-}
-
 // Gershgorin bounds of the spectrum: row k gives diag_k -/+ |cJ| sum_hops w sqrt((n_dst+1) n_src).  Used to scale
 // the Chebyshev filter of the accelerated solver (the upper bound must be rigorous: the filter explodes above it).
 __global__ void __launch_bounds__(256)
@@ -889,88 +541,20 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
     const bool prof_stored = (kernel_in == BH_HV_STORED || kernel_in == BH_HV_USER);
     BhProfScope prof(ctx, prof_stored ? BH_PROF_HV_STORED : BH_PROF_HV_FREE,
                      prof_stored ? 12.0 * (double)ctx->nnzH + 4.0 * (double)(D + 1) + 16.0 * (double)D : 16.0 * (double)ctx->nloc);
-    if (kernel == BH_HV_HYBRID) {
-        // only for chains on a single GPU; everything else runs the matrix-free kernel
-        if (ctx->partitioned || ctx->user_matrix || !ctx->h_tab.chain || ctx->hybrid_frac <= 0.0) {
-            kernel = BH_HV_MATRIX_FREE;
-        } else {
-            const int64_t Dh = ctx->D;
-            if (ctx->hyb_split < 0) {
-                BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu));  // builds the SELL copy
-                const int64_t win = ctx->sell_sigma;
-                int64_t split = (int64_t)(ctx->hybrid_frac * (double)Dh) / win * win;
-                split = std::min(split, Dh / win * win);
-                ctx->hyb_split = split;
-                ctx->hyb_slices = split / 32;
-                int ent = 0;
-                BH_D2H(ctx, &ent, ctx->d_sell_ptr + ctx->hyb_slices, sizeof(int));
-                BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                ctx->hyb_entries = ent;
-            }
-            BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu, ctx->hyb_entries, ctx->hyb_split));
-            hv_hybrid_fn_t fn = (ctx->h_tab.chain == 2) ? hv_hybrid_kernel<true>(ctx->m) : hv_hybrid_kernel<false>(ctx->m);
-            const int grid = ctx->sm_count * 8;  // a multiple of the role period (8)
-            fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, Dh, ctx->hyb_split, ctx->hyb_slices, ctx->hybrid_sell_blocks, ctx->d_sell_ptr,
-                                              ctx->d_sell_row, ctx->d_sell_col, ctx->d_sell_valH, ctx->d_states, ctx->d_dU, cJ, cU, cmu,
-                                              x, y, ep);
-            BH_LAUNCHED(ctx);
-            BH_CUDA(ctx, cudaGetLastError());
-            return BH_OK;
-        }
-    }
+    // BH_HV_HYBRID was a round-1 experiment (stored slices + matrix-free rows in one launch, not faster); the id is kept in
+    // the ABI and selects the matrix-free kernel
+    if (kernel == BH_HV_HYBRID) kernel = BH_HV_MATRIX_FREE;
     if (ctx->partitioned && kernel != BH_HV_MATRIX_FREE)
         return bh_fail(ctx, BH_ERR_STATE, "a row-partitioned context has no stored matrix: use BH_HV_MATRIX_FREE");
     if (ctx->user_matrix != (kernel == BH_HV_USER))
         return bh_fail(ctx, BH_ERR_STATE, "kernel BH_HV_USER needs bh_load_matrix, the other kernels need bh_setup");
-    if (kernel == BH_HV_USER || (kernel == BH_HV_STORED && ctx->hv_variant == 2)) {
+    if (kernel == BH_HV_USER || kernel == BH_HV_STORED) {
         if (kernel == BH_HV_STORED) BH_TRY(bh_materialise_sell(ctx, cJ, cU, cmu));
         const int64_t ns = ctx->sell_nslices;
         const int grid = (int)std::min<int64_t>((ns + 7) / 8, (int64_t)ctx->sm_count * 8);
         k_hv_sell<<<grid, 256, 0, ctx->stream>>>(D, ns, ctx->d_sell_ptr, ctx->d_sell_row, ctx->d_sell_col, ctx->d_sell_valH, x, y, ep);
         fused = true;
         BH_LAUNCHED(ctx);
-    } else if (kernel == BH_HV_STORED) {
-        BH_TRY(bh_materialise_H(ctx, cJ, cU, cmu));
-        const int64_t ntiles = (D + 31) / 32;
-        if (ctx->hv_variant == 1) {
-            if (ctx->tile_cap == 0) {
-                int* d_cap = nullptr;
-                BH_CUDA(ctx, cudaMalloc(&d_cap, sizeof(int)));
-                BH_CUDA(ctx, cudaMemsetAsync(d_cap, 0, sizeof(int), ctx->stream));
-                k_tile_cap<<<nblocks(ntiles, 256), 256, 0, ctx->stream>>>(D, ctx->d_rowptr, d_cap);
-                BH_LAUNCHED(ctx);
-                int cap = 0;
-                BH_D2H(ctx, &cap, d_cap, sizeof(int));
-                BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                cudaFree(d_cap);
-                ctx->tile_cap = (cap + 3) & ~3;
-            }
-            const int stages = ctx->hv_stages;
-            const size_t stage_bytes = (size_t)ctx->tile_cap * 12 + HVT_RP * 4;
-            const size_t smem = (size_t)HVT_WARPS * stages * stage_bytes + HVT_WARPS * stages * 8;
-            if (smem > 227 * 1024) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "H.v tile does not fit in shared memory");
-            void (*fn)(int64_t, const int*, const int*, const double*, const double*, double*, int) =
-                stages == 2 ? k_hv_csr_tma<2> : stages == 3 ? k_hv_csr_tma<3> : k_hv_csr_tma<4>;
-            if (ctx->hv_smem_configured != smem) {
-                BH_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ctx->hv_smem_configured = smem;
-            }
-            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024)));
-            const int grid = (int)std::min<int64_t>((ntiles + HVT_WARPS - 1) / HVT_WARPS, (int64_t)ctx->sm_count * per_sm);
-            fn<<<grid, HVT_WARPS * 32, smem, ctx->stream>>>(D, ctx->d_rowptr, ctx->d_col, ctx->d_valH, x, y, ctx->tile_cap);
-            BH_LAUNCHED(ctx);
-        } else {
-            const size_t smem = (size_t)HV_WARPS * 32 * ctx->max_row * sizeof(double);
-            if (smem > 48 * 1024 && ctx->hv_smem_configured != smem) {
-                BH_CUDA(ctx, cudaFuncSetAttribute(k_hv_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ctx->hv_smem_configured = smem;
-            }
-            int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
-            int grid = (int)std::min<int64_t>((ntiles + HV_WARPS - 1) / HV_WARPS, (int64_t)ctx->sm_count * per_sm);
-            k_hv_csr<<<grid, HV_WARPS * 32, smem, ctx->stream>>>(D, ctx->d_rowptr, ctx->d_col, ctx->d_valH, x, y,
-                                                                 ctx->max_row);
-            BH_LAUNCHED(ctx);
-        }
     } else if (kernel == BH_HV_MATRIX_FREE) {
         // row-partitioned context: x is the local slice; exchange it (NCCL all-gather) and read the full vector
         const double* xin = x;
@@ -986,7 +570,7 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
             const int grid = per_sm > 0 ? (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * per_sm)
                                         : (int)std::max<int64_t>(1, nblocks(nloc, 256));
             if (nloc > 0 && !(ablate & 2)) {
-                hv_free_fn_t f1 = closed ? hv_chain_part_kernel<true, 1>(ctx->m) : hv_chain_part_kernel<false, 1>(ctx->m);
+                hv_free_fn_t f1 = closed ? hv_chain_part_kernel<true>(ctx->m) : hv_chain_part_kernel<false>(ctx->m);
                 f1<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x - ctx->row0, y, ep);
                 BH_LAUNCHED(ctx);
             }
@@ -1004,24 +588,15 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
             xin = ctx->d_xfull;
         }
         if (nloc > 0) {
-            if (ctx->free_variant >= 2 && bh_split_supported(ctx)) {
-                BH_TRY(bh_launch_hv_split(ctx, cJ, cU, cmu, xin, y, ep));
-                fused = true;
-                ctx->launches--;  // counted by bh_launch_hv_split
-            } else if (ctx->free_variant >= 1 && ctx->h_tab.chain) {
+            if (ctx->h_tab.chain) {  // nearest-neighbour chain: single sweep over the sites
                 hv_free_fn_t fn = (ctx->h_tab.chain == 2) ? hv_chain_kernel<true>(ctx->m) : hv_chain_kernel<false>(ctx->m);
                 int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
                 fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y, ep);
-                fused = true;
-            } else if (ctx->free_variant >= 1) {
+            } else {  // any lattice: bond list
                 int grid = (int)std::min<int64_t>(nblocks(nloc, HVF_THREADS), (int64_t)ctx->sm_count * 5);
                 k_hv_free_bonds<<<grid, HVF_THREADS, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y, ep);
-                fused = true;
-            } else {
-                hv_free_fn fn = hv_free_kernel(ctx->m);
-                int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
-                fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, xin, y);
             }
+            fused = true;
             BH_LAUNCHED(ctx);
         }
     } else {

@@ -300,7 +300,6 @@ __global__ void k_fin_coef(double* __restrict__ scal, int i, int pass)
 // All partial sums are combined in a fixed order (deterministic).
 // ---------------------------------------------------------------------------------------------------------
 #define COOP_NP 10
-#define COOP_NP_S 6  // row pairs per thread of the shared-memory-residual form (3 CTAs per SM)
 #define COOP_THREADS 256
 
 __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ part, int n, int stride)
@@ -311,12 +310,14 @@ __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ p
     return bh_warp_sum(t);
 }
 
-// NP = row pairs per thread; FRS = the residual lives in shared memory instead of registers (85 instead of 128 registers:
-// three CTAs per SM, 24 warps instead of 16 -- the kernel is latency-bound, profiles/r01_ncu_final_kernels.md)
-template <int CH, int NP, bool FRS>
-__global__ void __launch_bounds__(COOP_THREADS, (FRS ? 3 : 2))
+// NP = row pairs per thread (the residual lives in registers: 128 registers, two CTAs per SM).  Variants measured and
+// removed in round 2: residual in shared memory with 3 CTAs per SM (-2 %), L2 prefetch of the next
+// block before the barrier (-1..-6 %), skipping the update of blocks with negligible coefficients (breaks the 1e-10 parity),
+// blocks of 4 columns (-3 %).
+template <int CH, int NP>
+__global__ void __launch_bounds__(COOP_THREADS, 2)
 k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, int passes, const double* __restrict__ w,
-            double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused, double tau, int pf)
+            double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[COOP_THREADS / 32][CH];
@@ -336,9 +337,8 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
 
     // ---- three-term update and alpha ----
     const double b = subtract ? scal[S_BETA + i] : 0.0;
-    extern __shared__ double2 s_fr[];  // [NP][COOP_THREADS] when FRS
-    double2 fr_reg[FRS ? 1 : NP];
-#define FR(t) (FRS ? s_fr[(t) * COOP_THREADS + threadIdx.x] : fr_reg[FRS ? 0 : (t)])
+    double2 fr_reg[NP];
+#define FR(t) fr_reg[t]
     double acc0 = 0.0;
 #pragma unroll
     for (int t = 0; t < NP; ++t) {
@@ -423,19 +423,6 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                     for (int q = 0; q < COOP_THREADS / 32; ++q) t += red[q][threadIdx.x];
                     pc[(int64_t)blockIdx.x * CH + threadIdx.x] = t;
                 }
-                if (pf > 0 && c0 + CH <= i) {
-                    // the sweep after the barrier starts with first-touch (HBM) loads of block c0 + CH: start them now so
-                    // that the barrier and the reduction hide their latency (one request per 128-byte line, no registers)
-                    const int ncp = min(CH, i + 1 - (c0 + CH));
-                    const double2* VP = V2 + (int64_t)(c0 + CH) * ld2;
-                    if ((lane & 7) == 0) {
-                        for (int t = 0; t < pf; ++t) {
-                            const int64_t p = gtid + t * gsz;
-                            if (p < npair)
-                                for (int j = 0; j < ncp; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(VP + (int64_t)j * ld2 + p));
-                        }
-                    }
-                }
                 grid.sync();
                 if (wid < nc) {
                     const double c = coop_sum_partials(pc + wid, nblk, CH);
@@ -447,19 +434,8 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                 double c[CH];
 #pragma unroll
                 for (int j = 0; j < CH; ++j) c[j] = cs[j];
-                // Coefficients below tau * beta change no bit pattern that matters (tau = 0: always update): the update sweep
-                // of such a block (a full re-read of its columns) is skipped; the decision is the same in every CTA.
-                bool apply = true;
-                if (tau > 0.0 && subtract && passes == 1) {
-                    double cmax = 0.0;
-#pragma unroll
-                    for (int j = 0; j < CH; ++j) cmax = fmax(cmax, fabs(c[j]));
-                    apply = !(cmax < tau * fabs(b));
-                }
-                if (apply) {
-                    if (i >= c0 && i < c0 + CH) alpha += cs[i - c0];                         // Lanczos.h:170
-                    if (subtract && i - 1 >= c0 && i - 1 < c0 + CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
-                }
+                if (i >= c0 && i < c0 + CH) alpha += cs[i - c0];                         // Lanczos.h:170
+                if (subtract && i - 1 >= c0 && i - 1 < c0 + CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
                 // update with block c0, dot products with block c0 + CH
                 const int c1 = c0 + CH;
                 const int nc1 = (c1 <= i) ? min(CH, i + 1 - c1) : 0;
@@ -472,15 +448,13 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                     const int64_t p = gtid + t * gsz;
                     if (p < npair) {
                         double2 v[CH];
-                        if (apply) {
-                            // last use of block c0 in this step: let L2 drop these lines first, block c0 + CH has to stay
+                        // last use of block c0 in this step: let L2 drop these lines first, block c0 + CH has to stay
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? __ldlu(VB + (int64_t)j * ld2 + p) : make_double2(0.0, 0.0);
+                        for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? __ldlu(VB + (int64_t)j * ld2 + p) : make_double2(0.0, 0.0);
 #pragma unroll
-                            for (int j = 0; j < CH; ++j) {
-                                FR(t).x = fma(-v[j].x, c[j], FR(t).x);
-                                FR(t).y = fma(-v[j].y, c[j], FR(t).y);
-                            }
+                        for (int j = 0; j < CH; ++j) {
+                            FR(t).x = fma(-v[j].x, c[j], FR(t).x);
+                            FR(t).y = fma(-v[j].y, c[j], FR(t).y);
                         }
                         if (nc1 > 0) {
 #pragma unroll
@@ -932,27 +906,12 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
 
     // cooperative single-launch step: needs every CTA resident and <= COOP_NP row pairs per thread
     int coop_grid = 0;
-    bool coop_smem = false;
     if (ctx->coop && !dist) {
         int bps = 0;
         const int64_t npair = (D + 1) / 2;
-        // residual in shared memory (3 CTAs per SM, COOP_NP_S pairs per thread) when it fits; else the register form
-        coop_smem = ctx->coop_smem && ctx->coop_ch != 4;
-        if (coop_smem) {
-            BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH, COOP_NP_S, true>, COOP_THREADS,
-                                                                        sizeof(double2) * COOP_NP_S * COOP_THREADS));
-            bps = std::min(bps, 3);
-            if (bps < 3 || npair > (int64_t)ctx->sm_count * bps * COOP_THREADS * COOP_NP_S) coop_smem = false;
-        }
-        if (!coop_smem) {
-            if (ctx->coop_ch == 4)
-                BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<4, COOP_NP, false>, COOP_THREADS, 0));
-            else
-                BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH, COOP_NP, false>, COOP_THREADS, 0));
-            bps = std::min(bps, 2);
-        }
-        const int coop_np = coop_smem ? COOP_NP_S : COOP_NP;
-        if (bps >= 1 && npair <= (int64_t)ctx->sm_count * bps * COOP_THREADS * coop_np) {
+        BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH, COOP_NP>, COOP_THREADS, 0));
+        bps = std::min(bps, 2);
+        if (bps >= 1 && npair <= (int64_t)ctx->sm_count * bps * COOP_THREADS * COOP_NP) {
             coop_grid = ctx->sm_count * bps;
             // do not spread a tiny problem over idle CTAs: grid syncs cost more with more CTAs
             const int64_t need = (npair + COOP_THREADS - 1) / COOP_THREADS;
@@ -998,12 +957,9 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
                 double* fv = ctx->d_f;
                 double th = near0;
                 int fused = ctx->coop_fused;
-                double tau = ctx->reorth_tau;
-                int pf = ctx->coop_prefetch;
-                void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused, &tau, &pf};
-                void* fn = coop_smem ? (void*)k_step_coop<GT_CH, COOP_NP_S, true>
-                                     : (ctx->coop_ch == 4 ? (void*)k_step_coop<4, COOP_NP, false> : (void*)k_step_coop<GT_CH, COOP_NP, false>);
-                const size_t fr_bytes = coop_smem ? sizeof(double2) * COOP_NP_S * COOP_THREADS : 0;
+                void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused};
+                void* fn = (void*)k_step_coop<GT_CH, COOP_NP>;
+                const size_t fr_bytes = 0;
                 {
                     // algorithmic bytes: w and the i + 1 basis columns read once, f and v_{i+1} written
                     BhProfScope prof(ctx, BH_PROF_STEP, 8.0 * (double)D * (i + 1 + 3));

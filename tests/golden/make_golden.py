@@ -42,6 +42,30 @@ if "--merge" in sys.argv:
     json.dump(meta, open(MFILE, "w"), indent=1, sort_keys=True)
     sys.exit(0)
 
+if "--dense" in sys.argv:
+    # --dense: for every golden grid point with D <= 5000, the 24 lowest eigenvalues by DENSE diagonalisation (numpy) of the
+    # same H (built by the oracle, whose H is bit-identical to the reference's: tests/test_oracle_vs_ref.py).  They show
+    # where the reference's single-vector Krylov solver misses copies of (>= 3-fold) degenerate levels.
+    import oracle_lib as O
+    old = dict(np.load(OUT))
+    for k in [k for k in old if k.startswith("point_") and k.endswith("_evals")]:
+        f = k[len("point_"):-len("_evals")].split("_")
+        m, n, cJ, cU, cu = int(f[0]), int(f[1]), float(f[2]), float(f[3]), float(f[4])
+        lat = f[5] if len(f) > 5 else "chain"
+        if O.dimension(m, n) > 5000:
+            continue
+        nbr = O.chain(m) if lat == "chain" else O.rect(*[int(v) for v in lat.split("-")[1:]])
+        t, b = O.basis(m, n)
+        o, i, v = O.hsum_csc(O.hopping_csc(m, nbr, t, b), *O.diagonals(m, b), cJ, cU, cu)
+        D = len(t)
+        H = np.zeros((D, D))
+        for c in range(D):
+            H[i[o[c]:o[c + 1]], c] = v[o[c]:o[c + 1]]
+        old[k[:-len("_evals")] + "_dense"] = np.linalg.eigvalsh(H)[:24]
+        print(k, "reference == dense:", bool(np.abs(np.sort(old[k]) - old[k[:-len("_evals")] + "_dense"][:20]).max() < 1e-9))
+    np.savez_compressed(OUT, **old)
+    sys.exit(0)
+
 if "--grid" in sys.argv:
     # --grid "m,n,fixed,cfix,p1min,p2min,step,n1,n2,lattice" --part FILE: a small sweep grid through the reference's
     # per-point body (ref_harness points), for lattices the reference CLI cannot build itself

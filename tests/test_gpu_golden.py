@@ -84,6 +84,11 @@ def test_points(pkg, ctx_factory, key):
     m, n, cJ, cU, cu, lat = parse_point_key(key)
     ctx = ctx_factory(m, n, nbr_of(pkg, lat, m))
     want = np.sort(G[f"point_{key}_evals"])
+    if f"point_{key}_dense" in G.files:
+        # Where dense diagonalisation of the same H is affordable the bar is the TRUTH.  It equals the reference's output at
+        # every fixture except the 4 x 3 torus with n = 3, where the reference's single-vector Krylov solver misses copies of
+        # two four-fold degenerate levels (tests/test_oracle_golden.py::test_reference_against_dense_truth pins that).
+        want = G[f"point_{key}_dense"][:20]
     scale = np.maximum(np.abs(want), np.abs(want[0]))
     rho = G[f"point_{key}_rho"]
     for kernel in (pkg.capi.HV_STORED, pkg.capi.HV_MATRIX_FREE):

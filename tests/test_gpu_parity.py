@@ -181,39 +181,3 @@ def test_error_behaviour(pkg, ctx_factory):
     assert ei.value.code == pkg.capi.ERR_ARG and "ncv must satisfy" in str(ei.value)
     with pytest.raises(pkg.BhError):
         pkg.Context(0).setup(17, 3)
-
-
-@pytest.mark.parametrize("m,n,closed", [(3, 3, True), (4, 5, True), (5, 5, False), (6, 6, True), (7, 9, True), (8, 8, True),
-                                        (8, 8, False), (10, 10, True), (3, 15, True), (16, 3, True)])
-def test_split_matrix_free_kernel(pkg, m, n, closed, monkeypatch):
-    """The split (prefix x suffix) matrix-free kernel (csrc/hv_split.cu) for every cut position and group size:
-    against the oracle (1e-13) where the oracle is quick, and against the per-row chain kernel everywhere."""
-    nbr = O.chain(m, closed)
-    otags, obas = O.basis(m, n, O.TAG_SORTED)
-    x = O.lcg_vector(len(otags))
-    pars = [(1.0, 4.0, 1.0), (0.3, 0.0, 2.0)]
-    want = None
-    if len(otags) <= 10000:
-        jc = O.hopping_csc(m, nbr, otags, obas, 1.0)
-        dU, dN = O.diagonals(m, obas)
-        want = [O.spmv(O.hsum_csc(jc, dU, dN, *p), x) for p in pars]
-    monkeypatch.setenv("BH_FREE_VARIANT", "1")
-    ctx = pkg.Context(0).setup(m, n, nbr)
-    chain = [ctx.hv(*p, x, kernel=pkg.capi.HV_MATRIX_FREE, order=pkg.capi.TAG_SORTED) for p in pars]
-    ctx.close()
-    if want is None:
-        want = chain
-    cuts = sorted({1, m // 2, m - 1} | ({m // 2 - 1, m // 2 + 1} & set(range(1, m))))
-    for p_cut in cuts:
-        for G, UJ in ((4, 2), (8, 1), (16, 1), (2, 4)) if p_cut == m // 2 else ((4, 2),):
-            monkeypatch.setenv("BH_FREE_VARIANT", "2")
-            monkeypatch.setenv("BH_SPLIT_P", str(p_cut))
-            monkeypatch.setenv("BH_SPLIT_G", str(G))
-            monkeypatch.setenv("BH_SPLIT_UJ", str(UJ))
-            ctx = pkg.Context(0).setup(m, n, nbr)
-            for k, p in enumerate(pars):
-                got = ctx.hv(*p, x, kernel=pkg.capi.HV_MATRIX_FREE, order=pkg.capi.TAG_SORTED)
-                scale = np.abs(want[k]).max()
-                assert np.abs(got - want[k]).max() <= 1e-13 * scale, (p_cut, G, UJ, np.abs(got - want[k]).max() / scale)
-                assert np.abs(got - chain[k]).max() <= 1e-13 * scale
-            ctx.close()

@@ -112,6 +112,21 @@ def test_point_rect_lattices(m, n, cJ, cU, cu, lat):
     assert_out3(r["out3"], G[key + "_out5"][2:], want, r["evals"])   # 4 x 3 / 3 x 3 tori: >= 3-fold degenerate levels
 
 
+def test_reference_against_dense_truth():
+    """Dense diagonalisation of the same H (fixtures `_dense`, tests/golden/make_golden.py --dense) for every golden point
+    with D <= 5000: the compiled reference returns the true 20 lowest levels with their multiplicities everywhere except on
+    the 4 x 3 torus with n = 3 (D = 364), where its single-vector Krylov solver finds 3 of 4 copies of the level 8.1117 and
+    2 of 4 copies of 10.1749 (copies of a degenerate level only enter through rounding).  The GPU tests hold the product to
+    the dense truth at that point."""
+    wrong = []
+    for k in G.files:
+        if k.startswith("point_") and k.endswith("_dense"):
+            ref = np.sort(G[k[:-len("_dense")] + "_evals"])
+            if np.abs(ref - G[k][:20]).max() > 1e-9 * max(1.0, np.abs(ref).max()):
+                wrong.append(k[len("point_"):-len("_dense")])
+    assert wrong == ["12_3_1_4_1_rect-4-3"], wrong
+
+
 def test_known_answers():
     # KA3 (SURVEY.md 8c): U = 0 -> E0 = -4 J n and the next level E0 + 4J(1 - cos 2pi/m), twice
     m = n = 6

@@ -19,7 +19,7 @@ D = ctx.D
 x = torch.empty(D, dtype=torch.float64, device="cuda"); y = torch.empty(D, dtype=torch.float64, device="cuda")
 ctx.lcg_fill_dev(x.data_ptr(), D)
 ref = None
-for name, kid in (("stored", capi.HV_STORED), ("free", capi.HV_MATRIX_FREE), ("hybrid", capi.HV_HYBRID)):
+for name, kid in (("stored", capi.HV_STORED), ("free", capi.HV_MATRIX_FREE)):
     if which not in (name, "both"): continue
     for _ in range(3): ctx.hv_dev(1.0, 4.0, 1.0, x.data_ptr(), y.data_ptr(), kid)
     torch.cuda.synchronize()
