@@ -420,6 +420,22 @@ def main():
         hv[name]["cold_ms"] = cold / nc
         hv[name]["cold_gbs"] = ab / (cold / nc * 1e-3) / 1e9
     del flush
+    # the MatOp seam (Spectra's perform_op: host pointers in and out): pageable vectors, then the same buffers page-locked
+    xh = np.random.default_rng(1).uniform(-0.5, 0.5, D)
+    yh = np.empty(D)
+    seam = {}
+    for label in ("pageable", "registered"):
+        if label == "registered" and not (capi.host_register(xh) and capi.host_register(yh)):
+            break
+        ctx.hv(1.0, 4.0, 1.0, xh, kernel=capi.HV_STORED, order=capi.LEX, out=yh)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctx.hv(1.0, 4.0, 1.0, xh, kernel=capi.HV_STORED, order=capi.LEX, out=yh)
+        seam[label + "_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+    if "registered_ms" in seam:
+        capi.host_unregister(xh)
+        capi.host_unregister(yh)
+    seam["bytes_each_way"] = int(D * 8)
     path.append({"kernel": KERNEL_NAMES["hv_stored"] + " alone, back to back (warm L2)", "class": "hv_stored_alone_warm", "bound": "hbm",
                  "launches": args.hv_reps, "ms_per_launch": hv["stored"]["ms"], "algorithmic_bytes_per_launch": hv["stored"]["algorithmic_bytes"],
                  "achieved": hv["stored"]["gbs"], "peak": peak, "unit": "GB/s", "frac": hv["stored"]["gbs"] / peak,
@@ -526,7 +542,7 @@ def main():
                         "mean_matvecs_per_point": int(np.mean(matvecs)) if matvecs else None, "setup_seconds": setup_s},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_path": path,
         "checks": checks,
-        "hv": {"stored": hv["stored"], "matrix_free": hv["matrix_free"]},
+        "hv": {"stored": hv["stored"], "matrix_free": hv["matrix_free"], "matop_seam_host_vectors": seam},
         "stored_kernel": stored, "small_configs": small,
     }
     if c5 is not None:

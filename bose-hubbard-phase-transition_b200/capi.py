@@ -25,7 +25,7 @@ SYMBOLS = [
     "bh_term_nnz", "bh_term_csc", "bh_hamiltonian_nnz", "bh_hamiltonian_csc", "bh_hv", "bh_hv_dev", "bh_eigs",
     "bh_spdm", "bh_gap_ratios", "bh_condensate_fraction", "bh_coherence", "bh_point", "bh_points",
     "bh_lcg_fill_dev", "bh_hv_algorithmic_bytes", "bh_load_matrix", "bh_ctx_set_batch",
-    "bh_ctx_profile_enable", "bh_ctx_profile_read", "bh_host_register", "bh_host_unregister",
+    "bh_ctx_profile_enable", "bh_ctx_profile_read", "bh_host_register", "bh_host_unregister", "bh_thermal_weights", "bh_density_matrix",
     "bh_dist_unique_id", "bh_dist_init", "bh_dist_finalize", "bh_setup_partitioned", "bh_partition",
 ]
 
@@ -85,6 +85,8 @@ def load():
     L.bh_point.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, C.POINTER(EigsInfo)]
     L.bh_points.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp]
     L.bh_ctx_set_batch.argtypes = [vp, C.c_int]
+    L.bh_thermal_weights.argtypes = [vp, C.c_int, C.c_double, vp]
+    L.bh_density_matrix.argtypes = [vp, C.c_int64, C.c_int, vp, vp, C.c_double, vp]
     L.bh_host_register.argtypes = [vp, C.c_int64]
     L.bh_host_unregister.argtypes = [vp]
     L.bh_ctx_profile_enable.argtypes = [vp, C.c_int]
@@ -103,6 +105,15 @@ def load():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def thermal_weights(evals, temperature):
+    e = np.ascontiguousarray(evals, dtype=np.float64)
+    w = np.empty(len(e))
+    rc = load().bh_thermal_weights(_ptr(e), len(e), float(temperature), _ptr(w))
+    if rc:
+        raise BhError(rc, "bh_thermal_weights: bad argument")
+    return w
 
 
 def host_register(a):
@@ -335,6 +346,15 @@ class Context:
             self._check(rc)
         return dict(evals=ev, vecs=vecs, nconv=info.nconv, nmatvec=info.nmatvec, nrestart=info.nrestart,
                     nreorth=info.nreorth, seconds=info.seconds, rc=rc)
+
+    def density_matrix(self, evals, vecs, temperature):
+        """rho = sum_k w_k u_k u_k^T (D x D) from eigenvectors given as rows of `vecs` (what eigs(want_vectors=True) returns)."""
+        e = np.ascontiguousarray(evals, dtype=np.float64)
+        u = np.ascontiguousarray(vecs, dtype=np.float64)   # [k][i] = column-major D x nev
+        D = u.shape[1]
+        rho = np.empty((D, D))
+        self._check(self.L.bh_density_matrix(self.h, D, len(e), _ptr(e), _ptr(u), float(temperature), _ptr(rho)))
+        return rho.T.copy()
 
     def spdm(self, phi, ncols=20, order=TAG_SORTED):
         phi = np.ascontiguousarray(phi, dtype=np.float64)

@@ -71,7 +71,6 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     if (const char* v = getenv("BH_CHEB_MARGIN")) ctx->cheb_margin = atof(v);
     if (const char* v = getenv("BH_CHEB_FRAC")) ctx->cheb_frac = atof(v);
     if (const char* v = getenv("BH_REORTH_BLOCK")) { ctx->reorth_block = std::min(BH_MAX_NCV, std::max(1, atoi(v))); ctx->reorth_block_forced = true; }
-    if (const char* v = getenv("BH_HV_STAGES")) ctx->hv_stages = std::min(4, std::max(2, atoi(v)));
     *out = ctx;
     return BH_OK;
 }
@@ -131,8 +130,6 @@ int bh_release_system(bh_ctx* ctx)
     free_dev(ctx->d_perm_tag); ctx->d_perm_tag = nullptr;
     free_dev(ctx->d_inv_tag); ctx->d_inv_tag = nullptr;
     bh_release_workspace(ctx);
-    ctx->tile_cap = 0;
-    ctx->hv_smem_configured = 0;
     ctx->valH_valid = false;
     ctx->m = ctx->n = 0;
     ctx->D = 0;

@@ -944,7 +944,7 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
                     BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_VF, i + 1));
                     k_fin_coef<<<1, 1, 0, st>>>(scal, i, pass);
                     k_gemv_n_norm<true><<<G, VEC_THREADS, 0, st>>>(D, ld, V, 0, i + 1, ctx->d_f, scal, i, part, counter, 1);
-                    BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_FLAG + 3, 1));
+                    if (pass == 1) BH_TRY(bh_dist_allreduce_sum(ctx, scal + S_FLAG + 3, 1));  // only the final norm is used
                 }
                 k_fin_sqrt<<<1, 1, 0, st>>>(scal, S_FLAG + 3, S_BETA + i + 1);
                 ctx->launches += 8;

@@ -208,6 +208,62 @@ extern "C" int bh_coherence(int m, const double* rho, double* out)
     return BH_OK;
 }
 
+// ---- finite-temperature branch (src/analysis.cpp:456-494) ----
+extern "C" int bh_thermal_weights(const double* evals, int nb_eigen, double temperature, double* weights)
+{
+    if (!evals || !weights || nb_eigen < 1 || !(temperature > 0.0)) return BH_ERR_ARG;
+    // :481  normalized = eigenvalues / max(eigenvalues);  :484  Z = sum exp(-beta normalized);  :486  w = exp(-beta normalized) / Z
+    double mx = evals[0];
+    for (int i = 1; i < nb_eigen; ++i) mx = std::max(mx, evals[i]);
+    const double beta = 1.0 / temperature;
+    double Z = 0.0;
+    for (int i = 0; i < nb_eigen; ++i) Z += std::exp(-beta * (evals[i] / mx));
+    for (int i = 0; i < nb_eigen; ++i) weights[i] = std::exp(-beta * (evals[i] / mx)) / Z;
+    return BH_OK;
+}
+
+// rho[i + j D] = sum_k w[k] U[i + k D] U[j + k D]  (16 x 16 tiles, the eigenvector slabs staged in shared memory)
+__global__ void __launch_bounds__(256)
+k_density_matrix(int64_t D, int nk, const double* __restrict__ U, const double* __restrict__ w, double* __restrict__ rho)
+{
+    __shared__ double ui[16][65], uj[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t i0 = (int64_t)blockIdx.x * 16, j0 = (int64_t)blockIdx.y * 16;
+    for (int idx = threadIdx.x; idx < 16 * nk; idx += 256) {
+        const int r = idx & 15, k = idx >> 4;
+        ui[r][k] = (i0 + r < D) ? U[i0 + r + (int64_t)k * D] * w[k] : 0.0;
+        uj[r][k] = (j0 + r < D) ? U[j0 + r + (int64_t)k * D] : 0.0;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    for (int k = 0; k < nk; ++k) acc = fma(ui[tx][k], uj[ty][k], acc);
+    if (i0 + tx < D && j0 + ty < D) rho[(i0 + tx) + (j0 + ty) * D] = acc;
+}
+
+extern "C" int bh_density_matrix(bh_ctx* ctx, int64_t D, int nb_eigen, const double* evals, const double* evecs, double temperature,
+                                 double* rho)
+{
+    if (!ctx || !evals || !evecs || !rho || D < 1 || nb_eigen < 1 || nb_eigen > 64) return bh_fail(ctx, BH_ERR_ARG, "bh_density_matrix: bad argument");
+    if (D > 46000) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "bh_density_matrix: the dense D x D matrix of the reference is limited to D <= 46000 here");
+    std::vector<double> w(nb_eigen);
+    if (bh_thermal_weights(evals, nb_eigen, temperature, w.data()) != BH_OK) return bh_fail(ctx, BH_ERR_ARG, "bh_density_matrix: temperature must be > 0");
+    BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dU = nullptr, *dw = nullptr, *drho = nullptr;
+    BH_CUDA(ctx, cudaMalloc(&dU, sizeof(double) * (size_t)D * nb_eigen));
+    BH_CUDA(ctx, cudaMalloc(&dw, sizeof(double) * nb_eigen));
+    BH_CUDA(ctx, cudaMalloc(&drho, sizeof(double) * (size_t)D * D));
+    BH_H2D(ctx, dU, evecs, sizeof(double) * (size_t)D * nb_eigen);
+    BH_H2D(ctx, dw, w.data(), sizeof(double) * nb_eigen);
+    dim3 grid((unsigned)((D + 15) / 16), (unsigned)((D + 15) / 16));
+    k_density_matrix<<<grid, 256, 0, ctx->stream>>>(D, nb_eigen, dU, dw, drho);
+    BH_LAUNCHED(ctx);
+    BH_CUDA(ctx, cudaGetLastError());
+    BH_D2H(ctx, rho, drho, sizeof(double) * (size_t)D * D);
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(dU); cudaFree(dw); cudaFree(drho);
+    return BH_OK;
+}
+
 // ---- one grid point / a shard of grid points ----
 extern "C" int bh_point(bh_ctx* ctx, double cJ, double cU, double cmu, int nb_eigen, int kernel, double* out3,
                         double* evals, double* rho, bh_eigs_info* info)

@@ -125,6 +125,14 @@ int bh_gap_ratios(const double* evals, int nb_eigen, double* ratios /* nb_eigen-
 int bh_condensate_fraction(int m, const double* rho, double* out);                       /* :331-334 */
 int bh_coherence(int m, const double* rho, double* out);                                 /* :542-556 */
 
+/* Finite-temperature branch of the sweep body (src/analysis.cpp:321-323, 456-494; dead code in the reference, whose
+ * temperature is the constant 0).  Boltzmann weights of the nb_eigen levels with the reference's normalisation (eigenvalues
+ * divided by their maximum before the exponential, :481-486); and the dense matrix the reference builds from them,
+ * rho = sum_k w_k u_k u_k^T (D x D, column-major, host) from D x nb_eigen eigenvectors (column-major, host; any basis order:
+ * the result is in the same order).  O(D^2) memory by construction: D up to a few 10^4. */
+int bh_thermal_weights(const double* evals, int nb_eigen, double temperature, double* weights);
+int bh_density_matrix(bh_ctx* ctx, int64_t D, int nb_eigen, const double* evals, const double* evecs, double temperature, double* rho);
+
 /* ---- sweep: replaces the body and loop of Analysis::calculate_and_save (src/analysis.cpp:266-387) */
 /* One grid point: eigensolve + gap ratio + SPDM + condensate fraction + coherence.
  * out3 = {gap_ratio, condensate_fraction, coherence}; evals[nb_eigen] and rho[m*m] optional. */

@@ -234,6 +234,34 @@ int main(int argc, char** argv)
                (t1 - t0) / (reps > 0 ? reps : 1), reps);
         return 0;
     }
+    if (cmd == "thermal") {
+        // thermal m n cJ cU cu T out : the finite-temperature branch of the sweep body (src/analysis.cpp:321-323, 474-494;
+        // dead in the reference, whose temperature is the constant 0): density_matrix(eigenvalues, eigenvectors, T) of the
+        // 20 Ritz pairs -- a dense D x D matrix -- and the two scalars the loop derives from it (:331-337).
+        int m = atoi(argv[2]), n = atoi(argv[3]);
+        double cJ = atof(argv[4]), cU = atof(argv[5]), cu = atof(argv[6]), T = atof(argv[7]);
+        std::string out = argv[8];
+        Terms t = build_terms(m, n, "chain");
+        Eigen::SparseMatrix<double> Hf = t.JH * cJ;
+        Eigen::SparseMatrix<double> H = Hf + t.UH * cU + t.uH * cu;
+        Eigen::MatrixXcd eigenvectors;
+        Eigen::VectorXcd eigenvalues = Op::IRLM_eigen(H, 20, eigenvectors);
+        Eigen::MatrixXcd dm = Analysis::density_matrix(eigenvalues, eigenvectors, T);
+        Eigen::MatrixXd re = dm.real();
+        Eigen::EigenSolver<Eigen::MatrixXd> solver(re);
+        double cf = std::abs(std::max_element(solver.eigenvalues().begin(), solver.eigenvalues().end(),
+                                              [](const std::complex<double>& a, const std::complex<double>& b) {
+                                                  return std::abs(a) < std::abs(b);
+                                              })->real() / dm.trace());
+        double K = Analysis::coherence(dm);
+        std::vector<double> ev(20), o2{cf, K};
+        for (int i = 0; i < 20; ++i) ev[i] = eigenvalues[i].real();
+        dump(out, "dm", re.data(), re.size());
+        dump(out, "evals", ev.data(), ev.size());
+        dump(out, "out2", o2.data(), o2.size());
+        printf("{\"D\": %ld}\n", (long)H.rows());
+        return 0;
+    }
     if (cmd == "maxbasis") {
         // maxbasis m n out : BH::max_set_basis (src/hamiltonian.cpp:152-166), all boson numbers 1..n, tag-sorted
         int m = atoi(argv[2]), n = atoi(argv[3]);

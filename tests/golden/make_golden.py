@@ -132,6 +132,12 @@ for term, (J, U, mu) in {"J": (1, 0, 0), "U": (0, 1.5, 0), "u": (0, 0, 0.75)}.it
     o, i, v = R.max_hamiltonian(4, 0, 2, J, U, mu)
     gold[f"maxham_{term}_4_0_2_outer"], gold[f"maxham_{term}_4_0_2_inner"], gold[f"maxham_{term}_4_0_2_val"] = o, i, v
 
+# --- finite-temperature branch (src/analysis.cpp:474-494): dense density matrix of the 20 Ritz pairs ---
+for (m, n, T) in [(5, 5, 0.5), (5, 5, 3.0), (6, 4, 1.0)]:
+    r = R.thermal(m, n, 1.0, 4.0, 1.0, T)
+    key = f"thermal_{m}_{n}_{T:g}"
+    gold[key + "_dm"], gold[key + "_evals"], gold[key + "_out2"] = r["dm"], r["evals"], r["out2"]
+
 # --- H.v through Spectra's MatOp ---
 for (m, n) in [(6, 6), (8, 8)]:
     r, _ = R.hv(m, n, 1.0, 4.0, 1.0)

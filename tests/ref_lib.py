@@ -81,6 +81,13 @@ def points(m, n, fixed, cfix, p1min, p2min, step, n1, n2, threads=0, lattice="ch
     return r, info
 
 
+def thermal(m, n, cJ, cU, cu, T):
+    info, r = _run(HARNESS, ["thermal", m, n, cJ, cU, cu, T, "@out"], [("dm", np.float64), ("evals", np.float64), ("out2", np.float64)])
+    D = info["D"]
+    r["dm"] = r["dm"].reshape(D, D).T
+    return r
+
+
 def max_basis(m, n):
     info, r = _run(HARNESS, ["maxbasis", m, n, "@out"], [("tags", np.float64), ("basis", np.float64)])
     return r["tags"], r["basis"].reshape(-1, m)
