@@ -577,7 +577,7 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
             }
             if (!(ablate & 1)) BH_TRY(bh_dist_halo_end(ctx));
             if (nloc > 0 && !(ablate & 4) && ctx->rem_nnz > 0) {
-                k_hv_remote<<<grid, 256, 0, ctx->stream>>>(nloc, ctx->d_rem_ptr, ctx->d_rem_col, ctx->d_rem_amp, ctx->d_xfull, y,
+                k_hv_remote<<<nblocks(nloc, 256), 256, 0, ctx->stream>>>(nloc, ctx->d_rem_ptr, ctx->d_rem_col, ctx->d_rem_amp, ctx->d_xfull, y,
                                                            ep.s1 * (-2.0 * cJ));
                 BH_LAUNCHED(ctx);
             }
