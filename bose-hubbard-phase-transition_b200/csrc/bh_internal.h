@@ -74,18 +74,21 @@ struct bh_ctx {
     bool partitioned = false;
     int64_t row0 = 0, nloc = 0;
     double* d_xfull = nullptr;  // all-gathered vector, world * ld doubles (global index = LEX rank)
-    // pipelined halo exchange (dist.cu): the slice is swept in `pieces` row ranges; before piece q only the chunks of the
-    // other slices that its hops read (and no earlier piece fetched) are exchanged, by grouped ncclSend / ncclRecv on a
-    // second communicator and a high-priority stream, while the earlier pieces are being computed
+    // overlapped halo exchange (dist.cu): only the chunks of the other slices that this rank's hops read are exchanged
+    // (ncclSend / ncclRecv on a second communicator and stream) while the own-slice hops are computed
     struct HaloRange { int peer; int64_t off, count; };  // off = global element offset
-    std::vector<std::vector<HaloRange>> halo_send, halo_recv;  // [piece]
-    std::vector<int64_t> halo_piece_off;                        // [pieces + 1] row offsets inside the slice
-    std::vector<cudaEvent_t> ev_piece;
+    std::vector<HaloRange> halo_send, halo_recv;
     void* nccl_comm2 = nullptr;
     cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_x_ready = nullptr;
+    cudaEvent_t ev_x_ready = nullptr, ev_halo_done = nullptr;
     bool halo_ready = false;
     int64_t halo_recv_elems = 0;
+    // the hops of this rank's rows whose source element lives in another rank's slice, stored once as a CSR matrix
+    // (pattern and amplitudes are fixed by the basis and the partition; 2J is applied at run time)
+    int* d_rem_ptr = nullptr;     // [nloc + 1]
+    int* d_rem_col = nullptr;     // global LEX rank of the source
+    double* d_rem_amp = nullptr;  // sqrt((n_dst + 1) n_src)
+    int64_t rem_nnz = 0;
     std::vector<int> nbr_ptr, nbr_idx;
     BhTables h_tab;
     BhTables* d_tab = nullptr;
@@ -240,11 +243,12 @@ int bh_spdm_dev(bh_ctx* ctx, const double* phi_dev, int ncols, double* rho_host)
 // NCCL plumbing (dist.cu; libnccl is dlopen'ed on first use)
 int bh_dist_allreduce_sum(bh_ctx* ctx, double* buf_dev, int64_t count);
 int bh_dist_allgather(bh_ctx* ctx, const double* send_dev, double* recv_dev, int64_t count_per_rank);
-int bh_mark_halo_chunks(bh_ctx* ctx, int64_t off, int64_t cnt, unsigned char* flags_dev);  // hv.cu: rows [off, off + cnt) of the slice
+int bh_mark_halo_chunks(bh_ctx* ctx, unsigned char* flags_dev);  // hv.cu
+int bh_build_remote_hops(bh_ctx* ctx);                           // hv.cu: d_rem_* (chains, partitioned)
 int bh_exclusive_scan(bh_ctx* ctx, int64_t n, const int* d_in, int* d_out, int64_t* total);  // csr.cu: out[0..n]
 int bh_dist_plan_halo(bh_ctx* ctx);                              // once per bh_setup_partitioned (chains)
-int bh_dist_halo_begin(bh_ctx* ctx, const double* x_local);      // enqueue the exchange of every piece (communication stream)
-int bh_dist_halo_wait(bh_ctx* ctx, int piece);                   // the context's stream waits for the data of one piece
+int bh_dist_halo_begin(bh_ctx* ctx, const double* x_local);      // start the exchange of x into d_xfull (communication stream)
+int bh_dist_halo_end(bh_ctx* ctx);                               // the context's stream waits for it
 void bh_dist_release_halo(bh_ctx* ctx);
 
 // host-side small dense symmetric eigen-decomposition (ascending; vectors in columns of v, column-major)

@@ -9,7 +9,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <string>
 
 #include "bh_internal.h"
 
@@ -90,10 +89,15 @@ extern "C" int bh_dist_init(bh_ctx* ctx, int world, int rank, const void* id128)
 
 void bh_dist_release_halo(bh_ctx* ctx)
 {
+    if (ctx->d_rem_ptr) cudaFree(ctx->d_rem_ptr);
+    if (ctx->d_rem_col) cudaFree(ctx->d_rem_col);
+    if (ctx->d_rem_amp) cudaFree(ctx->d_rem_amp);
+    ctx->d_rem_ptr = ctx->d_rem_col = nullptr;
+    ctx->d_rem_amp = nullptr;
+    ctx->rem_nnz = 0;
     ctx->halo_ready = false;
     ctx->halo_send.clear();
     ctx->halo_recv.clear();
-    ctx->halo_piece_off.clear();
     ctx->halo_recv_elems = 0;
 }
 
@@ -108,9 +112,8 @@ extern "C" int bh_dist_finalize(bh_ctx* ctx)
         cudaStreamDestroy(ctx->comm_stream);
         ctx->comm_stream = nullptr;
         if (ctx->ev_x_ready) cudaEventDestroy(ctx->ev_x_ready);
-        ctx->ev_x_ready = nullptr;
-        for (cudaEvent_t e : ctx->ev_piece) cudaEventDestroy(e);
-        ctx->ev_piece.clear();
+        if (ctx->ev_halo_done) cudaEventDestroy(ctx->ev_halo_done);
+        ctx->ev_x_ready = ctx->ev_halo_done = nullptr;
     }
     if (ctx->nccl_comm) {
         cudaStreamSynchronize(ctx->stream);
@@ -150,17 +153,13 @@ int bh_dist_allgather(bh_ctx* ctx, const double* send, double* recv, int64_t cou
 
 
 // ---------------------------------------------------------------------------------------------------------
-// Pipelined halo exchange for the row-partitioned matrix-free H.v (chains).  The ncclAllGather of the whole vector
-// (world * ld doubles into every rank, every H.v) is what made two GPUs slower than one in round 1: a rank's hops only read
-// part of the other slices, and nothing was overlapped.  Here a rank sweeps its slice in `pieces` row ranges.  Once per
-// bh_setup_partitioned every rank marks, per piece, the 4096-row chunks of the global vector that the hops of that piece
-// read outside the slice (k_mark_halo_chain); the flag arrays are all-gathered and each rank derives, per piece, the ranges
-// it must receive (chunks no earlier piece already fetched) and the ranges it must send to every peer.  Per H.v the pieces'
-// ranges travel as `pieces` grouped ncclSend / ncclRecv batches on a SECOND communicator and a high-priority stream, from
-// the caller's local vector straight into d_xfull at their global offsets; the context's stream waits for batch q only
-// before sweeping piece q, so the exchange of the later pieces hides behind the sweep of the earlier ones.  Because a hop
-// across bond (q, q+1) shifts the LEX rank monotonically, consecutive row pieces read (mostly) consecutive remote ranges:
-// measured on the hop graph the new chunks per piece are roughly total / pieces (tools/halo_fraction.py).
+// Overlapped halo exchange for the row-partitioned matrix-free H.v (chains).  The ncclAllGather of the whole vector
+// (world * ld doubles into every rank, every H.v) is what made two GPUs slower than one; a rank's hops only read
+// part of the other slices.  Once per bh_setup_partitioned every rank marks the 4096-row chunks its hops read
+// (k_mark_halo_chain), the flag arrays are all-gathered, and each rank derives the ranges it must send to / receive
+// from every peer.  Per H.v the ranges travel by grouped ncclSend / ncclRecv on a SECOND communicator and stream,
+// straight from the caller's local vector into d_xfull at their global offsets, while the context's stream computes the
+// hops whose source is local (k_hv_free_chain_part<.., 1>); the remote hops follow once the exchange has completed.
 // ---------------------------------------------------------------------------------------------------------
 #define HALO_CHUNK 4096
 
@@ -172,7 +171,6 @@ int bh_dist_plan_halo(bh_ctx* ctx)
     if (!g_nccl.CommSplit) return BH_OK;             // old NCCL: keep the all-gather path
     BH_CUDA(ctx, cudaSetDevice(ctx->device));
     const int W = ctx->world;
-    const int NP = std::max(1, std::min(16, getenv("BH_HALO_PIECES") ? atoi(getenv("BH_HALO_PIECES")) : 4));
     const int64_t per = ctx->ld;  // slice length (equal on every rank, a multiple of 32)
     const int64_t nchunks = (per * W + HALO_CHUNK - 1) / HALO_CHUNK;
     if (!ctx->comm_stream) {
@@ -183,45 +181,25 @@ int bh_dist_plan_halo(bh_ctx* ctx)
         BH_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         BH_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
         BH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_x_ready, cudaEventDisableTiming));
+        BH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo_done, cudaEventDisableTiming));
     }
-    while ((int)ctx->ev_piece.size() < NP) {
-        cudaEvent_t e;
-        BH_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        ctx->ev_piece.push_back(e);
-    }
-    // row pieces of this rank's slice (multiples of 256 rows)
-    ctx->halo_piece_off.assign(NP + 1, ctx->nloc);
-    for (int q = 0; q < NP; ++q) ctx->halo_piece_off[q] = std::min<int64_t>(ctx->nloc, (ctx->nloc * q / NP) / 256 * 256);
-    // flags of every (rank, piece): [W][NP][nchunks] bytes
-    const size_t per_rank = (size_t)NP * nchunks;
+    // flags of every rank: [W][nchunks] bytes
     unsigned char* d_flags = nullptr;
-    BH_CUDA(ctx, cudaMalloc(&d_flags, per_rank * W));
-    BH_CUDA(ctx, cudaMemsetAsync(d_flags, 0, per_rank * W, ctx->stream));
-    for (int q = 0; q < NP; ++q)
-        BH_TRY(bh_mark_halo_chunks(ctx, ctx->halo_piece_off[q], ctx->halo_piece_off[q + 1] - ctx->halo_piece_off[q],
-                                   d_flags + (size_t)ctx->rank * per_rank + (size_t)q * nchunks));
-    BH_NCCL(ctx, g_nccl.AllGather(d_flags + (size_t)ctx->rank * per_rank, d_flags, per_rank, ncclUint8,
+    BH_CUDA(ctx, cudaMalloc(&d_flags, (size_t)nchunks * W));
+    BH_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)nchunks * W, ctx->stream));
+    BH_TRY(bh_mark_halo_chunks(ctx, d_flags + (size_t)ctx->rank * nchunks));
+    BH_NCCL(ctx, g_nccl.AllGather(d_flags + (size_t)ctx->rank * nchunks, d_flags, (size_t)nchunks, ncclUint8,
                                   static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));
-    std::vector<unsigned char> flags(per_rank * W);
+    std::vector<unsigned char> flags((size_t)nchunks * W);
     BH_D2H(ctx, flags.data(), d_flags, flags.size());
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_flags);
-    // piece q of a reader fetches the chunks it reads that none of its earlier pieces fetched
-    for (int r = 0; r < W; ++r)
-        for (int64_t c = 0; c < nchunks; ++c) {
-            bool seen = false;
-            for (int q = 0; q < NP; ++q) {
-                unsigned char& f = flags[(size_t)r * per_rank + (size_t)q * nchunks + c];
-                if (f && seen) f = 0;
-                seen = seen || f;
-            }
-        }
-    // ranges of rank `owner`'s slice that piece q of rank `reader` fetches: runs of flagged chunks clipped to the owner's
-    // slice; runs separated by fewer than 4 clean chunks are merged (fewer, larger messages)
-    auto ranges = [&](int reader, int q, int owner, std::vector<bh_ctx::HaloRange>& out, int peer) {
+    // ranges of rank `owner`'s slice that rank `reader` reads: runs of flagged chunks clipped to the owner's slice;
+    // runs separated by fewer than 8 clean chunks are merged (fewer, larger messages)
+    auto ranges = [&](int reader, int owner, std::vector<bh_ctx::HaloRange>& out, int peer) {
         const int64_t lo = per * owner, hi = std::min<int64_t>(ctx->D, per * (owner + 1));
         if (hi <= lo) return;
-        const unsigned char* f = flags.data() + (size_t)reader * per_rank + (size_t)q * nchunks;
+        const unsigned char* f = flags.data() + (size_t)reader * nchunks;
         const int64_t c0 = lo / HALO_CHUNK, c1 = (hi + HALO_CHUNK - 1) / HALO_CHUNK;
         int64_t run0 = -1, last = -1;
         auto flush = [&]() {
@@ -232,36 +210,26 @@ int bh_dist_plan_halo(bh_ctx* ctx)
         };
         for (int64_t c = c0; c < c1; ++c) {
             if (!f[c]) continue;
-            if (run0 >= 0 && c - last > 4) flush();
+            if (run0 >= 0 && c - last > 8) flush();
             if (run0 < 0) run0 = c;
             last = c;
         }
         flush();
     };
-    ctx->halo_send.assign(NP, {});
-    ctx->halo_recv.assign(NP, {});
+    for (int p = 0; p < W; ++p) {
+        if (p == ctx->rank) continue;
+        ranges(ctx->rank, p, ctx->halo_recv, p);  // what I read from p's slice
+        ranges(p, ctx->rank, ctx->halo_send, p);  // what p reads from mine
+    }
     ctx->halo_recv_elems = 0;
-    size_t nranges = 0;
-    for (int q = 0; q < NP; ++q) {
-        for (int p = 0; p < W; ++p) {
-            if (p == ctx->rank) continue;
-            ranges(ctx->rank, q, p, ctx->halo_recv[q], p);  // what my piece q reads from p's slice
-            ranges(p, q, ctx->rank, ctx->halo_send[q], p);  // what p's piece q reads from mine
-        }
-        for (const auto& r : ctx->halo_recv[q]) ctx->halo_recv_elems += r.count;
-        nranges += ctx->halo_recv[q].size();
-    }
+    for (const auto& r : ctx->halo_recv) ctx->halo_recv_elems += r.count;
+    BH_TRY(bh_build_remote_hops(ctx));
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->halo_ready = true;
-    if (getenv("BH_DIST_VERBOSE")) {
-        std::string per_piece;
-        for (int q = 0; q < NP; ++q) {
-            int64_t e = 0;
-            for (const auto& r : ctx->halo_recv[q]) e += r.count;
-            per_piece += " " + std::to_string(e * 8 / 1000000) + "MB";
-        }
-        fprintf(stderr, "[bh] rank %d halo plan: %d pieces, %zu recv ranges, %.1f MB = %.3f D per H.v; per piece:%s\n", ctx->rank, NP, nranges,
-                ctx->halo_recv_elems * 8e-6, (double)ctx->halo_recv_elems / (double)ctx->D, per_piece.c_str());
-    }
+    if (getenv("BH_DIST_VERBOSE"))
+        fprintf(stderr, "[bh] rank %d halo plan: %zu recv ranges (%.1f MB = %.3f D), %zu send ranges, %.2f remote hops per row\n", ctx->rank,
+                ctx->halo_recv.size(), ctx->halo_recv_elems * 8e-6, (double)ctx->halo_recv_elems / (double)ctx->D, ctx->halo_send.size(),
+                (double)ctx->rem_nnz / (double)std::max<int64_t>(ctx->nloc, 1));
     return BH_OK;
 }
 
@@ -272,23 +240,18 @@ int bh_dist_halo_begin(bh_ctx* ctx, const double* x_local)
     BH_CUDA(ctx, cudaEventRecord(ctx->ev_x_ready, ctx->stream));
     BH_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x_ready, 0));
     ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm2);
-    const int NP = (int)ctx->halo_recv.size();
-    for (int q = 0; q < NP; ++q) {
-        if (!ctx->halo_send[q].empty() || !ctx->halo_recv[q].empty()) {
-            BH_NCCL(ctx, g_nccl.GroupStart());
-            for (const auto& r : ctx->halo_send[q])
-                BH_NCCL(ctx, g_nccl.Send(x_local + (r.off - ctx->row0), (size_t)r.count, ncclDouble, r.peer, comm, ctx->comm_stream));
-            for (const auto& r : ctx->halo_recv[q])
-                BH_NCCL(ctx, g_nccl.Recv(ctx->d_xfull + r.off, (size_t)r.count, ncclDouble, r.peer, comm, ctx->comm_stream));
-            BH_NCCL(ctx, g_nccl.GroupEnd());
-        }
-        BH_CUDA(ctx, cudaEventRecord(ctx->ev_piece[q], ctx->comm_stream));
-    }
+    BH_NCCL(ctx, g_nccl.GroupStart());
+    for (const auto& r : ctx->halo_send)
+        BH_NCCL(ctx, g_nccl.Send(x_local + (r.off - ctx->row0), (size_t)r.count, ncclDouble, r.peer, comm, ctx->comm_stream));
+    for (const auto& r : ctx->halo_recv)
+        BH_NCCL(ctx, g_nccl.Recv(ctx->d_xfull + r.off, (size_t)r.count, ncclDouble, r.peer, comm, ctx->comm_stream));
+    BH_NCCL(ctx, g_nccl.GroupEnd());
+    BH_CUDA(ctx, cudaEventRecord(ctx->ev_halo_done, ctx->comm_stream));
     return BH_OK;
 }
 
-int bh_dist_halo_wait(bh_ctx* ctx, int piece)
+int bh_dist_halo_end(bh_ctx* ctx)
 {
-    BH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_piece[piece], 0));
+    BH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo_done, 0));
     return BH_OK;
 }

@@ -172,18 +172,71 @@ k_hv_free_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, cons
     }
 }
 
+// Row-partitioned form of the chain kernel (one large eigensolve over several GPUs, BASELINE.json config 5): the hops of a
+// row are split by where their source element lives.  This kernel takes the hops whose source is in this rank's own slice
+// [row0, row0 + D) -- x is then the LOCAL slice, addressed through a pointer shifted by -row0 -- plus the diagonal and the
+// epilogue, and runs while the halo exchange is in flight: the single sweep of k_hv_free_chain with a range test per hop.
+// The hops whose source lies in another rank's slice are a stored CSR matrix applied afterwards (k_hv_remote).
+template <int M, bool CLOSED>
+__global__ void __launch_bounds__(256, CHAIN_MIN_BLOCKS)
+k_hv_free_chain_part(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
+                     const double* __restrict__ dU, double cJ, double cU, double cmu, const double* __restrict__ x,
+                     double* __restrict__ y, BhEpilogue ep)
+{
+    __shared__ BhTables t;
+    bh_stage_tables(&t, gtab);
+    const double shift = __dmul_rn(-(double)t.n, cmu);
+    const unsigned lo = (unsigned)row0, len = (unsigned)D;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = row0 + l;
+        const uint64_t s = states[l];
+        const int kk = (int)k;
+        const int n0 = bh_occ(s, 0);
+        int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
+        double acc = 0.0;
+        auto hop = [&](int cond, int tgt, double amp) {
+            const bool local = ((unsigned)tgt - lo) < len;
+            const bool take = cond && local;
+            const double xv = take ? __ldg(x + tgt) : 0.0;
+            acc = fma(amp, xv, acc);
+        };
+#pragma unroll
+        for (int q = 0; q < M - 1; ++q) {
+            const int nnext = bh_occ(s, q + 1);
+            const int2 gh = t.gh[q][R];
+            hop(nnext, kk + gh.x, t.sq[(nprev + 1) * nnext]);
+            hop(nprev, kk + gh.y, t.sq[(nnext + 1) * nprev]);
+            tdn += gh.x;
+            tup += gh.y;
+            R -= nnext;
+            nprev = nnext;
+        }
+        if (CLOSED) {
+            const int nl = nprev;
+            hop(nl, kk + tdn, t.sq[(n0 + 1) * nl]);
+            hop(n0, kk + tup, t.sq[(nl + 1) * n0]);
+        }
+        const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
+        const double xv = x[k];
+        double out = ep.s1 * (diag * xv - (2.0 * cJ) * acc);
+        if (ep.s2 != 0.0) out = fma(ep.s2, xv, out);
+        if (ep.z) out = fma(ep.s3, ep.z[l], out);
+        y[l] = out;
+    }
+}
+
 // Which 4096-row chunks of the global vector hold a source element of some hop of this rank's rows: flags[chunk] = 1
 // (the halo plan of dist.cu is built from these flags once per bh_setup_partitioned).
 #define HALO_CHUNK_SHIFT 12
 template <int M, bool CLOSED>
 __global__ void __launch_bounds__(256)
-k_mark_halo_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, int64_t off, int64_t cnt,
-                  const uint64_t* __restrict__ states, unsigned char* __restrict__ flags)
+k_mark_halo_chain(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
+                  unsigned char* __restrict__ flags)
 {
     __shared__ BhTables t;
     bh_stage_tables(&t, gtab);
     const unsigned lo = (unsigned)row0, len = (unsigned)D;
-    for (int64_t l = off + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < off + cnt; l += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t s = states[l];
         const int kk = (int)(row0 + l);
         const int n0 = bh_occ(s, 0);
@@ -232,7 +285,29 @@ static hv_free_fn_t hv_chain_kernel(int m)
 }
 
 
-typedef void (*mark_fn_t)(const BhTables*, int64_t, int64_t, int64_t, int64_t, const uint64_t*, unsigned char*);
+template <bool CLOSED>
+static hv_free_fn_t hv_chain_part_kernel(int m)
+{
+    switch (m) {
+        case 3: return k_hv_free_chain_part<3, CLOSED>;
+        case 4: return k_hv_free_chain_part<4, CLOSED>;
+        case 5: return k_hv_free_chain_part<5, CLOSED>;
+        case 6: return k_hv_free_chain_part<6, CLOSED>;
+        case 7: return k_hv_free_chain_part<7, CLOSED>;
+        case 8: return k_hv_free_chain_part<8, CLOSED>;
+        case 9: return k_hv_free_chain_part<9, CLOSED>;
+        case 10: return k_hv_free_chain_part<10, CLOSED>;
+        case 11: return k_hv_free_chain_part<11, CLOSED>;
+        case 12: return k_hv_free_chain_part<12, CLOSED>;
+        case 13: return k_hv_free_chain_part<13, CLOSED>;
+        case 14: return k_hv_free_chain_part<14, CLOSED>;
+        case 15: return k_hv_free_chain_part<15, CLOSED>;
+        case 16: return k_hv_free_chain_part<16, CLOSED>;
+    }
+    return nullptr;
+}
+
+typedef void (*mark_fn_t)(const BhTables*, int64_t, int64_t, const uint64_t*, unsigned char*);
 template <bool CLOSED>
 static mark_fn_t mark_halo_kernel(int m)
 {
@@ -255,15 +330,127 @@ static mark_fn_t mark_halo_kernel(int m)
     return nullptr;
 }
 
+// The remote hops of every local row as a CSR matrix (built once per bh_setup_partitioned): MODE 0 counts them per row,
+// MODE 1 writes (source rank, amplitude) at the scanned offsets, in the order of the sweep.
+template <int M, bool CLOSED, int MODE>
+__global__ void __launch_bounds__(256)
+k_remote_hops(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
+              int* __restrict__ ptr_or_count, int* __restrict__ col, double* __restrict__ amp)
+{
+    __shared__ BhTables t;
+    bh_stage_tables(&t, gtab);
+    const unsigned lo = (unsigned)row0, len = (unsigned)D;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = states[l];
+        const int kk = (int)(row0 + l);
+        const int n0 = bh_occ(s, 0);
+        int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
+        int pos = (MODE == 1) ? ptr_or_count[l] : 0;
+        auto hop = [&](int cond, int tgt, int code) {
+            if (cond && !(((unsigned)tgt - lo) < len)) {
+                if (MODE == 1) {
+                    col[pos] = tgt;
+                    amp[pos] = t.sq[code];
+                }
+                ++pos;
+            }
+        };
+#pragma unroll
+        for (int q = 0; q < M - 1; ++q) {
+            const int nnext = bh_occ(s, q + 1);
+            const int2 gh = t.gh[q][R];
+            hop(nnext, kk + gh.x, (nprev + 1) * nnext);
+            hop(nprev, kk + gh.y, (nnext + 1) * nprev);
+            tdn += gh.x;
+            tup += gh.y;
+            R -= nnext;
+            nprev = nnext;
+        }
+        if (CLOSED) {
+            const int nl = nprev;
+            hop(nl, kk + tdn, (n0 + 1) * nl);
+            hop(n0, kk + tup, (nl + 1) * n0);
+        }
+        if (MODE == 0) ptr_or_count[l] = pos;
+    }
+}
+
+// y[l] += coef * sum_e amp[e] x[col[e]] over the remote hops of row l (x = the exchanged full-length buffer)
+__global__ void __launch_bounds__(256)
+k_hv_remote(int64_t D, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ amp,
+            const double* __restrict__ x, double* __restrict__ y, double coef)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= D) return;
+    const int a = __ldg(ptr + l), b = __ldg(ptr + l + 1);
+    if (a == b) return;
+    double acc = 0.0;
+    for (int e = a; e < b; ++e) acc = fma(__ldcs(amp + e), __ldg(x + __ldcs(col + e)), acc);
+    y[l] = fma(coef, acc, y[l]);
+}
+
+typedef void (*remote_fn_t)(const BhTables*, int64_t, int64_t, const uint64_t*, int*, int*, double*);
+template <bool CLOSED, int MODE>
+static remote_fn_t remote_hops_kernel(int m)
+{
+    switch (m) {
+        case 3: return k_remote_hops<3, CLOSED, MODE>;
+        case 4: return k_remote_hops<4, CLOSED, MODE>;
+        case 5: return k_remote_hops<5, CLOSED, MODE>;
+        case 6: return k_remote_hops<6, CLOSED, MODE>;
+        case 7: return k_remote_hops<7, CLOSED, MODE>;
+        case 8: return k_remote_hops<8, CLOSED, MODE>;
+        case 9: return k_remote_hops<9, CLOSED, MODE>;
+        case 10: return k_remote_hops<10, CLOSED, MODE>;
+        case 11: return k_remote_hops<11, CLOSED, MODE>;
+        case 12: return k_remote_hops<12, CLOSED, MODE>;
+        case 13: return k_remote_hops<13, CLOSED, MODE>;
+        case 14: return k_remote_hops<14, CLOSED, MODE>;
+        case 15: return k_remote_hops<15, CLOSED, MODE>;
+        case 16: return k_remote_hops<16, CLOSED, MODE>;
+    }
+    return nullptr;
+}
+
+int bh_build_remote_hops(bh_ctx* ctx)
+{
+    if (ctx->d_rem_ptr) { cudaFree(ctx->d_rem_ptr); ctx->d_rem_ptr = nullptr; }
+    if (ctx->d_rem_col) { cudaFree(ctx->d_rem_col); ctx->d_rem_col = nullptr; }
+    if (ctx->d_rem_amp) { cudaFree(ctx->d_rem_amp); ctx->d_rem_amp = nullptr; }
+    ctx->rem_nnz = 0;
+    const int64_t nloc = ctx->nloc;
+    const bool closed = ctx->h_tab.chain == 2;
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_rem_ptr, sizeof(int) * (size_t)(nloc + 1)));
+    BH_CUDA(ctx, cudaMemsetAsync(ctx->d_rem_ptr, 0, sizeof(int) * (size_t)(nloc + 1), ctx->stream));
+    if (nloc == 0) return BH_OK;
+    int* d_cnt = nullptr;
+    BH_CUDA(ctx, cudaMalloc(&d_cnt, sizeof(int) * (size_t)nloc));
+    const int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
+    remote_fn_t f0 = closed ? remote_hops_kernel<true, 0>(ctx->m) : remote_hops_kernel<false, 0>(ctx->m);
+    f0<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, d_cnt, nullptr, nullptr);
+    BH_LAUNCHED(ctx);
+    int64_t total = 0;
+    BH_TRY(bh_exclusive_scan(ctx, nloc, d_cnt, ctx->d_rem_ptr, &total));
+    cudaFree(d_cnt);
+    if (total >= ((int64_t)1 << 31)) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "remote hop matrix: more than 2^31 entries");
+    ctx->rem_nnz = total;
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_rem_col, sizeof(int) * (size_t)std::max<int64_t>(total, 1)));
+    BH_CUDA(ctx, cudaMalloc(&ctx->d_rem_amp, sizeof(double) * (size_t)std::max<int64_t>(total, 1)));
+    remote_fn_t f1 = closed ? remote_hops_kernel<true, 1>(ctx->m) : remote_hops_kernel<false, 1>(ctx->m);
+    f1<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_rem_ptr, ctx->d_rem_col, ctx->d_rem_amp);
+    BH_LAUNCHED(ctx);
+    BH_CUDA(ctx, cudaGetLastError());
+    return BH_OK;
+}
+
 // flags_dev[(world * ld) >> 12 chunks] <- 1 where this rank's rows read a remote chunk (chains only); see dist.cu
-int bh_mark_halo_chunks(bh_ctx* ctx, int64_t off, int64_t cnt, unsigned char* flags_dev)
+int bh_mark_halo_chunks(bh_ctx* ctx, unsigned char* flags_dev)
 {
     if (!ctx->h_tab.chain || ctx->m < 3) return bh_fail(ctx, BH_ERR_UNSUPPORTED, "halo plan: chains only");
-    if (cnt <= 0) return BH_OK;
-    // "remote" = outside this rank's whole slice; rows [off, off + cnt) of the slice are swept
+    if (ctx->nloc == 0) return BH_OK;
     mark_fn_t fn = (ctx->h_tab.chain == 2) ? mark_halo_kernel<true>(ctx->m) : mark_halo_kernel<false>(ctx->m);
-    const int grid = (int)std::min<int64_t>(nblocks(cnt, 256), (int64_t)ctx->sm_count * 8);
-    fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, ctx->nloc, off, cnt, ctx->d_states, flags_dev);
+    const int grid = (int)std::min<int64_t>(nblocks(ctx->nloc, 256), (int64_t)ctx->sm_count * 8);
+    fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, ctx->nloc, ctx->d_states, flags_dev);
     BH_LAUNCHED(ctx);
     BH_CUDA(ctx, cudaGetLastError());
     return BH_OK;
@@ -373,25 +560,25 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
         const double* xin = x;
         const int64_t nloc = ctx->nloc;
         if (ctx->partitioned && ctx->halo_ready && ctx->h_tab.chain && ctx->m >= 3) {
-            // Pipelined halo exchange (dist.cu): the slice is swept in row pieces; piece q only waits for the parts of the other
-            // slices that ITS hops read (and no earlier piece already fetched), which travel on the communication stream while
-            // the earlier pieces are being computed.  Every piece is the ordinary single sweep over a full-length buffer.
-            static const int ablate = getenv("BH_HALO_ABLATE") ? atoi(getenv("BH_HALO_ABLATE")) : 0;  // timing probes only: 1 no exchange, 2 no sweep
-            static const int per_sm = getenv("BH_HALO_GRID") ? atoi(getenv("BH_HALO_GRID")) : 7;  // CTAs per SM: one slot is left to the exchange kernel
-            const bool closed = ctx->h_tab.chain == 2;
-            BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_xfull + ctx->row0, x, sizeof(double) * (size_t)nloc, cudaMemcpyDeviceToDevice, ctx->stream));
+            // overlapped form: halo exchange on the communication stream, own-slice hops meanwhile, remote hops afterwards
+            static const int ablate = getenv("BH_HALO_ABLATE") ? atoi(getenv("BH_HALO_ABLATE")) : 0;  // timing probes only
             if (!(ablate & 1)) BH_TRY(bh_dist_halo_begin(ctx, x));
-            hv_free_fn_t fn = closed ? hv_chain_kernel<true>(ctx->m) : hv_chain_kernel<false>(ctx->m);
-            const int np = (int)ctx->halo_piece_off.size() - 1;
-            for (int q = 0; q < np; ++q) {
-                const int64_t off = ctx->halo_piece_off[q], cnt = ctx->halo_piece_off[q + 1] - off;
-                if (!(ablate & 1)) BH_TRY(bh_dist_halo_wait(ctx, q));
-                if (cnt <= 0 || (ablate & 2)) continue;
-                BhEpilogue epq = ep;
-                if (epq.z) epq.z += off;
-                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks(cnt, 256), (int64_t)ctx->sm_count * std::max(per_sm, 1)));
-                fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0 + off, cnt, ctx->d_states + off, ctx->d_dU + off, cJ, cU, cmu, ctx->d_xfull,
-                                                  y + off, epq);
+            const bool closed = ctx->h_tab.chain == 2;
+            // a persistent grid of 7 CTAs per SM: the eighth slot of every SM stays free for the exchange kernel of the
+            // (high-priority) communication stream, so that the two really overlap.  Measured at m = n = 14 on 2 GPUs: 8 per SM
+            // serialises the exchange behind the sweep (596 us per H.v), one CTA per 256 rows 386 us, 7 per SM 331 us, 6: 349, 4: 419.
+            static const int per_sm = getenv("BH_HALO_GRID") ? atoi(getenv("BH_HALO_GRID")) : 7;  // 0: one CTA per 256 rows
+            const int grid = per_sm > 0 ? (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * per_sm)
+                                        : (int)std::max<int64_t>(1, nblocks(nloc, 256));
+            if (nloc > 0 && !(ablate & 2)) {
+                hv_free_fn_t f1 = closed ? hv_chain_part_kernel<true>(ctx->m) : hv_chain_part_kernel<false>(ctx->m);
+                f1<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x - ctx->row0, y, ep);
+                BH_LAUNCHED(ctx);
+            }
+            if (!(ablate & 1)) BH_TRY(bh_dist_halo_end(ctx));
+            if (nloc > 0 && !(ablate & 4) && ctx->rem_nnz > 0) {
+                k_hv_remote<<<nblocks(nloc, 256), 256, 0, ctx->stream>>>(nloc, ctx->d_rem_ptr, ctx->d_rem_col, ctx->d_rem_amp, ctx->d_xfull, y,
+                                                           ep.s1 * (-2.0 * cJ));
                 BH_LAUNCHED(ctx);
             }
             BH_CUDA(ctx, cudaGetLastError());
