@@ -564,10 +564,13 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
             static const int ablate = getenv("BH_HALO_ABLATE") ? atoi(getenv("BH_HALO_ABLATE")) : 0;  // timing probes only
             if (!(ablate & 1)) BH_TRY(bh_dist_halo_begin(ctx, x));
             const bool closed = ctx->h_tab.chain == 2;
-            // a persistent grid of 7 CTAs per SM: the eighth slot of every SM stays free for the exchange kernel of the
-            // (high-priority) communication stream, so that the two really overlap.  Measured at m = n = 14 on 2 GPUs: 8 per SM
-            // serialises the exchange behind the sweep (596 us per H.v), one CTA per 256 rows 386 us, 7 per SM 331 us, 6: 349, 4: 419.
-            static const int per_sm = getenv("BH_HALO_GRID") ? atoi(getenv("BH_HALO_GRID")) : 7;  // 0: one CTA per 256 rows
+            // one CTA per 256 rows (not a persistent grid): the exchange kernel on the high-priority communication stream gets
+            // SM slots as soon as the first CTAs retire, so that the two really overlap.  Measured at m = n = 14 on 2 GPUs (per
+            // H.v): a persistent grid of 8 CTAs per SM serialises the exchange behind the sweep (596 us), 7 per SM leaves no room
+            // for an NCCL CTA either (~420 us), one CTA per 256 rows 386 us = sweep 268 (with the 202 us exchange hidden) + remote
+            // hops 92 + 26 exposed.  A pipelined variant (row pieces waiting only for their own remote chunks, one ordinary sweep
+            // per piece) was built and measured slower: 4 grouped ncclSend/Recv batches take 334 us against 202 us for one.
+            static const int per_sm = getenv("BH_HALO_GRID") ? atoi(getenv("BH_HALO_GRID")) : 0;  // > 0: persistent CTAs per SM
             const int grid = per_sm > 0 ? (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * per_sm)
                                         : (int)std::max<int64_t>(1, nblocks(nloc, 256));
             if (nloc > 0 && !(ablate & 2)) {
