@@ -134,7 +134,6 @@ struct bh_ctx {
     int hv_block_cols = 0;
     double* d_gram_part = nullptr;   // per-CTA partial Gram matrices
     int compress_tiled = 2;  // restart GEMM (env BH_COMPRESS_TILED): 0 shared-memory rows, 1 4x4 register tiles, 2 4x8 register tiles
-    int coop_ring = 1;     // cooperative step: HBM-streamed columns through a per-thread cp.async ring in shared memory (env BH_COOP_RING)
     int coop_fused = 1;    // cooperative step: update with block k fused with the dot products of block k+1 (env BH_COOP_FUSED)
     int coop = 1;          // single cooperative launch per Lanczos step when the residual fits in registers (env BH_COOP)
     int reorth_block = 8;  // basis columns per re-orthogonalisation block (env BH_REORTH_BLOCK)

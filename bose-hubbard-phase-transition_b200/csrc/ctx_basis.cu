@@ -63,7 +63,6 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
     if (const char* v = getenv("BH_SELL_SIGMA")) ctx->sell_sigma = std::min(1024, std::max(32, atoi(v) / 32 * 32));
     if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
     if (const char* v = getenv("BH_COOP_FUSED")) ctx->coop_fused = atoi(v);
-    if (const char* v = getenv("BH_COOP_RING")) ctx->coop_ring = atoi(v);
     if (const char* v = getenv("BH_RR_GRAM")) ctx->rr_gram = atoi(v);
     if (const char* v = getenv("BH_COMPRESS_TILED")) ctx->compress_tiled = atoi(v);
     if (const char* v = getenv("BH_CHEB_DEGREE")) ctx->cheb_degree = std::max(1, atoi(v));

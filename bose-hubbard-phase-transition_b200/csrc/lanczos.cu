@@ -301,16 +301,6 @@ __global__ void k_fin_coef(double* __restrict__ scal, int i, int pass)
 // ---------------------------------------------------------------------------------------------------------
 #define COOP_NP 10
 #define COOP_THREADS 256
-#define COOP_RING 3  // stages of the per-thread cp.async ring (3 x 32 KB per CTA, two CTAs per SM)
-
-__device__ __forceinline__ void bh_cp_async16(void* smem, const void* gmem)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void bh_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bh_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ part, int n, int stride)
 {
@@ -324,7 +314,7 @@ __device__ __forceinline__ double coop_sum_partials(const double* __restrict__ p
 // removed in round 2: residual in shared memory with 3 CTAs per SM (-2 %), L2 prefetch of the next
 // block before the barrier (-1..-6 %), skipping the update of blocks with negligible coefficients (breaks the 1e-10 parity),
 // blocks of 4 columns (-3 %).
-template <int CH, int NP, int RING>
+template <int CH, int NP>
 __global__ void __launch_bounds__(COOP_THREADS, 2)
 k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, int passes, const double* __restrict__ w,
             double* __restrict__ f, double* __restrict__ scal, double* __restrict__ part, double thresh, int fused)
@@ -399,46 +389,19 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
     // (streamed from HBM) run in the same sweep over the rows, so the two memory levels are busy together instead of in
     // turn; same arithmetic, same order of operations per row, one grid.sync per block as before.
     if (fused) {
-        // RING > 0: the columns streamed from HBM (the dot-product operands of the NEXT block) do not go through registers:
-        // every thread copies its own 16-byte pieces with cp.async into a private RING-deep ring in shared memory, RING - 1
-        // row pairs ahead of their use, and the first stages of a block are issued BEFORE the grid barrier that precedes it.
-        // ncu (profiles/r02_ncu_kernels.md): the register form is latency-bound (DRAM 49 % busy, 16 warps per SM, long-
-        // scoreboard stalls); the ring keeps RING x 32 KB per CTA in flight without holding registers.
-        extern __shared__ __align__(16) double2 ring[];  // [RING][CH][COOP_THREADS]
-        auto ring_slot = [&](int t, int j) -> double2* { return ring + ((size_t)((t % (RING > 0 ? RING : 1)) * CH + j) * COOP_THREADS + threadIdx.x); };
-        auto ring_issue = [&](int t, const double2* base, int ncols) {  // one commit group per row pair, empty past the end
-            if (RING > 0) {
-                const int64_t p = gtid + (int64_t)t * gsz;
-                if (t < NP && p < npair) {
-#pragma unroll
-                    for (int j = 0; j < CH; ++j)
-                        if (j < ncols) bh_cp_async16(ring_slot(t, j), base + (int64_t)j * ld2 + p);
-                }
-                bh_cp_async_commit();
-            }
-        };
         for (int pass = 0; pass < passes; ++pass) {
             double acc[CH];
 #pragma unroll
             for (int j = 0; j < CH; ++j) acc[j] = 0.0;
             {
                 const int nc = min(CH, i + 1);
-                if (RING > 0) {
-#pragma unroll
-                    for (int t = 0; t < RING - 1; ++t) ring_issue(t, V2, nc);
-                }
 #pragma unroll
                 for (int t = 0; t < NP; ++t) {
                     const int64_t p = gtid + t * gsz;
-                    if (RING > 0) {
-                        ring_issue(t + RING - 1, V2, nc);
-                        bh_cp_async_wait<(RING > 0 ? RING - 1 : 0)>();
-                    }
                     if (p < npair) {
                         double2 v[CH];
 #pragma unroll
-                        for (int j = 0; j < CH; ++j)
-                            v[j] = (j < nc) ? (RING > 0 ? *ring_slot(t, j) : V2[(int64_t)j * ld2 + p]) : make_double2(0.0, 0.0);
+                        for (int j = 0; j < CH; ++j) v[j] = (j < nc) ? V2[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
                         for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, FR(t).x, fma(v[j].y, FR(t).y, acc[j]));
                     }
@@ -446,10 +409,6 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
             }
             for (int c0 = 0; c0 <= i; c0 += CH) {
                 const int nc = min(CH, i + 1 - c0);
-                const int c1 = c0 + CH;
-                const int nc1 = (c1 <= i) ? min(CH, i + 1 - c1) : 0;
-                const double2* VB = V2 + (int64_t)c0 * ld2;
-                const double2* VN = V2 + (int64_t)c1 * ld2;
                 // finish the dot products of block c0
 #pragma unroll
                 for (int j = 0; j < CH; ++j) acc[j] = bh_warp_sum(acc[j]);
@@ -463,11 +422,6 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                     double t = 0.0;
                     for (int q = 0; q < COOP_THREADS / 32; ++q) t += red[q][threadIdx.x];
                     pc[(int64_t)blockIdx.x * CH + threadIdx.x] = t;
-                }
-                // the first row pairs of the next block start their trip from HBM now: they land during the barrier
-                if (RING > 0 && nc1 > 0) {
-#pragma unroll
-                    for (int t = 0; t < RING - 1; ++t) ring_issue(t, VN, nc1);
                 }
                 grid.sync();
                 if (wid < nc) {
@@ -483,15 +437,15 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                 if (i >= c0 && i < c0 + CH) alpha += cs[i - c0];                         // Lanczos.h:170
                 if (subtract && i - 1 >= c0 && i - 1 < c0 + CH) offd += cs[i - 1 - c0];  // Lanczos.h:168
                 // update with block c0, dot products with block c0 + CH
+                const int c1 = c0 + CH;
+                const int nc1 = (c1 <= i) ? min(CH, i + 1 - c1) : 0;
+                const double2* VB = V2 + (int64_t)c0 * ld2;
+                const double2* VN = V2 + (int64_t)c1 * ld2;
 #pragma unroll
                 for (int j = 0; j < CH; ++j) acc[j] = 0.0;
 #pragma unroll
                 for (int t = 0; t < NP; ++t) {
                     const int64_t p = gtid + t * gsz;
-                    if (RING > 0 && nc1 > 0) {
-                        ring_issue(t + RING - 1, VN, nc1);
-                        bh_cp_async_wait<(RING > 0 ? RING - 1 : 0)>();
-                    }
                     if (p < npair) {
                         double2 v[CH];
                         // last use of block c0 in this step: let L2 drop these lines first, block c0 + CH has to stay
@@ -504,8 +458,7 @@ k_step_coop(int64_t D, int64_t ld, double* __restrict__ V, int i, int subtract, 
                         }
                         if (nc1 > 0) {
 #pragma unroll
-                            for (int j = 0; j < CH; ++j)
-                                v[j] = (j < nc1) ? (RING > 0 ? *ring_slot(t, j) : VN[(int64_t)j * ld2 + p]) : make_double2(0.0, 0.0);
+                            for (int j = 0; j < CH; ++j) v[j] = (j < nc1) ? VN[(int64_t)j * ld2 + p] : make_double2(0.0, 0.0);
 #pragma unroll
                             for (int j = 0; j < CH; ++j) acc[j] = fma(v[j].x, FR(t).x, fma(v[j].y, FR(t).y, acc[j]));
                         }
@@ -953,16 +906,10 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
 
     // cooperative single-launch step: needs every CTA resident and <= COOP_NP row pairs per thread
     int coop_grid = 0;
-    const size_t coop_ring_bytes = sizeof(double2) * COOP_RING * GT_CH * COOP_THREADS;
     if (ctx->coop && !dist) {
         int bps = 0;
         const int64_t npair = (D + 1) / 2;
-        if (ctx->coop_ring) {
-            BH_CUDA(ctx, cudaFuncSetAttribute(k_step_coop<GT_CH, COOP_NP, COOP_RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_ring_bytes));
-            BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH, COOP_NP, COOP_RING>, COOP_THREADS, coop_ring_bytes));
-            if (bps < 2) ctx->coop_ring = 0;  // the ring must not cost the second CTA of an SM
-        }
-        if (!ctx->coop_ring) BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH, COOP_NP, 0>, COOP_THREADS, 0));
+        BH_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_step_coop<GT_CH, COOP_NP>, COOP_THREADS, 0));
         bps = std::min(bps, 2);
         if (bps >= 1 && npair <= (int64_t)ctx->sm_count * bps * COOP_THREADS * COOP_NP) {
             coop_grid = ctx->sm_count * bps;
@@ -1011,8 +958,8 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
                 double th = near0;
                 int fused = ctx->coop_fused;
                 void* args[] = {&Dv, &ldv, &V, &ii, &sub, &npass, &wv, &fv, &scal, &part, &th, &fused};
-                void* fn = (ctx->coop_ring && fused) ? (void*)k_step_coop<GT_CH, COOP_NP, COOP_RING> : (void*)k_step_coop<GT_CH, COOP_NP, 0>;
-                const size_t fr_bytes = (ctx->coop_ring && fused) ? coop_ring_bytes : 0;
+                void* fn = (void*)k_step_coop<GT_CH, COOP_NP>;
+                const size_t fr_bytes = 0;
                 {
                     // algorithmic bytes: w and the i + 1 basis columns read once, f and v_{i+1} written
                     BhProfScope prof(ctx, BH_PROF_STEP, 8.0 * (double)D * (i + 1 + 3));
