@@ -63,6 +63,8 @@ def test_density_matrix_against_reference(pkg, ctx_factory, m, n, T):
     assert np.abs(dm - dm.T).max() <= 1e-15 and abs(np.trace(dm) - 1.0) <= 1e-12
     assert np.abs(dm - (V.T * w) @ V).max() <= 1e-14     # the kernel computes sum_k w_k u_k u_k^T
     for g in groups(r["evals"]):
+        if 19 in g:
+            continue   # the 20th level may be one half of a degenerate pair cut by nev: its eigenvector is then not unique
         P = V[g].T @ V[g]                                 # eigenspace projector
         # trace of the reference's matrix over every eigenspace = the group's total weight (see the module docstring)
         assert abs(np.trace(P @ ref) - w[g].sum()) <= 1e-9 * w[g].sum(), g
