@@ -29,8 +29,6 @@ Eigen::VectorXcd Op::IRLM_eigen(Eigen::SparseMatrix<double> O, int nb_eigen, Eig
     if (rc != BH_OK) throw std::runtime_error("Eigenvalue computation failed.");
     Eigen::VectorXcd out(nb_eigen);
     for (int i = 0; i < nb_eigen; ++i) out[i] = std::complex<double>(evals[i], 0.0);
-    eigenvectors.resize(D, nb_eigen);
-    for (int j = 0; j < nb_eigen; ++j)
-        for (int64_t i = 0; i < D; ++i) eigenvectors(i, j) = std::complex<double>(vecs[(size_t)j * D + i], 0.0);
+    eigenvectors = Eigen::Map<const Eigen::MatrixXd>(vecs.data(), D, nb_eigen).cast<std::complex<double>>();
     return out;
 }

@@ -3,7 +3,7 @@ the reference's range plumbing / grid arithmetic / phase.txt format, and the sha
 
 Follows Analysis::exact_parameters and calculate_and_save (reference src/analysis.cpp:242-256, :281-282,
 :303-308, :341, :364-387).  The C++ host layer (host/analysis.cpp) implements the same logic for the CLI;
-tests/test_cli.py checks both against the golden phase.txt files.
+tests/test_shim.py checks both against the golden phase.txt files.
 """
 import numpy as np
 
