@@ -5,7 +5,7 @@
 
 Workload (config 3 of BASELINE.json, SURVEY.md section 8d "C3"): closed chain m = 12 sites, n = 12 bosons
 (D = 1 352 078, nnz(H) = 18 282 446), the 32 x 32 grid of `-J 1 -U 0 -u 0 -r 31 -s 1 -f J`
-(J-coefficient 1, U-coefficient 1..32, mu 0..31).  A step = one list of P (default 8) grid points per GPU (eigensolve for
+(J-coefficient 1, U-coefficient 1..32, mu 0..31).  A step = one list of P (default 16, the CLI's chunk) grid points per GPU (eigensolve for
 the 20 lowest levels + gap ratio + SPDM + condensate fraction + coherence; the points of a list are solved in lockstep and
 share their H.v launches, --batch, results identical point by point); every rank gets the same U values (a fixed
 pseudo-random order over the grid's 32) at different mu; per-GPU work is fixed as N grows (weak scaling, no data-path
@@ -226,7 +226,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points-per-step", type=int, default=8)
+    ap.add_argument("--points-per-step", type=int, default=16)
     ap.add_argument("--batch", type=int, default=4,
                     help="grid points solved in lockstep per GPU (bh_ctx_set_batch): their Chebyshev-filter H.v launches are shared")
     ap.add_argument("--kernel", default="free", choices=["stored", "free"],

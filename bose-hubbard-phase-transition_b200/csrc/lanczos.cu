@@ -673,10 +673,10 @@ k_compress_tiled(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k, 
         for (int cb = 0; cb < 4; ++cb) {
             const int c = cgp * 4 + cb;
             if (c < nck) {
-                double* dst = V + (int64_t)(c0 + c) * ld + r0 + rg * 4;
+                double* dst = V + (int64_t)(c0 + c) * ld + r0 + rg;
 #pragma unroll
                 for (int ra = 0; ra < 4; ++ra)
-                    if (r0 + rg * 4 + ra < D) dst[ra] = acc[ra][cb];
+                    if (r0 + rg + 64 * ra < D) dst[64 * ra] = acc[ra][cb];
             }
         }
     }
@@ -693,7 +693,7 @@ k_compress_tiled8(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k,
     double* vt = sm3;                            // [ncv][CT8_ROWS]
     double* yc = sm3 + (size_t)ncv * CT8_ROWS;   // [ncv][CT_COLS]
     const int64_t r0 = (int64_t)blockIdx.x * CT8_ROWS;
-    const int rg = threadIdx.x & 63, cgp = threadIdx.x >> 6;  // 64 row groups (4 rows) x 4 column groups (8 columns)
+    const int rg = threadIdx.x & 63, cgp = threadIdx.x >> 6;  // 64 row groups (rows rg, rg + 64, rg + 128, rg + 192) x 4 column groups (8 columns)
     for (int idx = threadIdx.x; idx < ncv * CT8_ROWS; idx += blockDim.x) {
         const int j = idx / CT8_ROWS, r = idx % CT8_ROWS;
         vt[idx] = (r0 + r < D) ? V[(int64_t)j * ld + r0 + r] : 0.0;
@@ -712,9 +712,11 @@ k_compress_tiled8(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k,
 #pragma unroll
             for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
         for (int j = 0; j < ncv; ++j) {
-            const double2 a01 = *reinterpret_cast<const double2*>(vt + j * CT8_ROWS + rg * 4);
-            const double2 a23 = *reinterpret_cast<const double2*>(vt + j * CT8_ROWS + rg * 4 + 2);
-            const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+            // the 4 rows of a thread are 64 apart: consecutive lanes read consecutive doubles (conflict-free; 4 consecutive rows per
+            // thread made every 128-bit load a 2-way bank conflict: 14.5 M conflicts per launch under ncu) and the stores coalesce
+            double a[4];
+#pragma unroll
+            for (int ra = 0; ra < 4; ++ra) a[ra] = vt[j * CT8_ROWS + rg + 64 * ra];
             double b[8];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -731,10 +733,10 @@ k_compress_tiled8(int64_t D, int64_t ld, double* __restrict__ V, int ncv, int k,
         for (int cb = 0; cb < 8; ++cb) {
             const int c = cgp * 8 + cb;
             if (c < nck) {
-                double* dst = V + (int64_t)(c0 + c) * ld + r0 + rg * 4;
+                double* dst = V + (int64_t)(c0 + c) * ld + r0 + rg;
 #pragma unroll
                 for (int ra = 0; ra < 4; ++ra)
-                    if (r0 + rg * 4 + ra < D) dst[ra] = acc[ra][cb];
+                    if (r0 + rg + 64 * ra < D) dst[64 * ra] = acc[ra][cb];
             }
         }
     }
