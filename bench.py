@@ -47,7 +47,6 @@ KERNEL_NAMES = {
     "hv_free": "k_hv_free_chain<12> (matrix-free H.v, one vector)",
     "hv_batch2": "k_hv_chain_batch<12,2> (matrix-free H.v, 2 lockstep vectors)",
     "hv_batch4": "k_hv_chain_batch<12,4> (matrix-free H.v, 4 lockstep vectors)",
-    "hv_batch8": "k_hv_chain_batch<12,8> (matrix-free H.v, 8 lockstep vectors)",
     "hv_stored": "k_hv_sell (stored H.v, SELL-32)",
     "step": "k_step_coop<8> (Lanczos step: three-term update + full re-orthogonalisation + normalisation)",
     "restart": "k_compress_tiled8 (thick restart V <- V Y)",
@@ -398,7 +397,7 @@ def main():
     notes = {
         "step": "bytes = 8 D (k + 3): w and the k basis columns read once, f and v_{k} written (k = columns orthogonalised against, 21..41)",
         "hv_batch4": "bytes = 4 x 16 D (SURVEY.md 8d matrix-free figure per vector); L1/issue-bound at m=n=12: x is L2-resident",
-        "hv_batch8": "bytes = 8 x 16 D", "hv_batch2": "bytes = 2 x 16 D", "hv_free": "bytes = 16 D", "restart": "bytes = 8 D (ncv + k_kept)",
+        "hv_batch2": "bytes = 2 x 16 D", "hv_free": "bytes = 16 D", "restart": "bytes = 8 D (ncv + k_kept)",
         "gram": "bytes = 16 D ncv", "spdm": "bytes = 16 D m",
     }
     path = [entry(k, v, notes.get(k)) for k, v in prof.items() if v["launches"] > 0]

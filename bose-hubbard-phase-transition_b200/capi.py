@@ -16,7 +16,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOCONV, ERR_UNSUPPORTED = 0, -1, -2, -3, -
 LEX, TAG_SORTED, REF_SCATTER = 0, 1, 2
 TERM_J, TERM_U, TERM_MU = 0, 1, 2
 HV_STORED, HV_MATRIX_FREE, HV_USER, HV_HYBRID = 0, 1, 2, 3
-PROF_CLASSES = ["hv_free", "hv_batch2", "hv_batch4", "hv_stored", "step", "restart", "gram", "spdm", "small", "hv_batch8"]
+PROF_CLASSES = ["hv_free", "hv_batch2", "hv_batch4", "hv_stored", "step", "restart", "gram", "spdm", "small"]
 
 # every symbol include/bh_b200.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [
@@ -206,7 +206,7 @@ class Context:
         self._check(self.L.bh_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
     def set_batch(self, batch):
-        """bh_points solves `batch` (1..8) grid points in lockstep, sharing their H.v launches."""
+        """bh_points solves `batch` (1..4) grid points in lockstep, sharing their H.v launches."""
         self._check(self.L.bh_ctx_set_batch(self.h, int(batch)))
         return self
 

@@ -21,7 +21,7 @@
 #include "device_utils.cuh"
 #include "lockstep_sched.h"
 
-#define BH_MAX_BATCH 8
+#define BH_MAX_BATCH 4
 
 struct BatchReq {
     const double* x = nullptr;
@@ -63,21 +63,6 @@ __device__ __forceinline__ void load_il(const double* __restrict__ base, int idx
 __device__ __forceinline__ void store_il(double* base, size_t row, const double (&v)[4])
 {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(base + row * 4), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
-}
-
-// eight interleaved doubles: two 256-bit accesses
-__device__ __forceinline__ void load_il(const double* __restrict__ base, int idx, double (&v)[8])
-{
-    const double* p = base + (size_t)idx * 8;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7]) : "l"(p + 4));
-}
-
-__device__ __forceinline__ void store_il(double* base, size_t row, const double (&v)[8])
-{
-    double* p = base + row * 8;
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7]) : "memory");
 }
 
 __device__ __forceinline__ void store_il(double* base, size_t row, const double (&v)[2])
@@ -198,7 +183,6 @@ static batch_fn batch_kernel(int m, int nb, bool src_il)
     if (nb == 2) return src_il ? batch_kernel_m<2, true, 4>(m) : batch_kernel_m<2, false, 4>(m);
     if (nb == 4 && minb4 == 4) return src_il ? batch_kernel_m<4, true, 4>(m) : batch_kernel_m<4, false, 4>(m);
     if (nb == 4) return src_il ? batch_kernel_m<4, true, 3>(m) : batch_kernel_m<4, false, 3>(m);
-    if (nb == 8) return src_il ? batch_kernel_m<8, true, 2>(m) : batch_kernel_m<8, false, 2>(m);
     return nullptr;
 }
 
@@ -208,7 +192,7 @@ bool bh_batch_supported(const bh_ctx* ctx, int kernel)
            ctx->m <= 16 && ctx->cheb_degree > 1 && !ctx->parent;
 }
 
-// The Chebyshev filters of the parked fibers fib[0..nb), nb in {2, 4, 8}, applied together (see bh_lanczos, stage 2).
+// The Chebyshev filters of the parked fibers fib[0..nb), nb in {2, 4}, applied together (see bh_lanczos, stage 2).
 static int apply_filters(bh_ctx* parent, bh_batch_hub* hub, const int* fib, int nb)
 {
     const int m = parent->m;
@@ -242,7 +226,7 @@ static int apply_filters(bh_ctx* parent, bh_batch_hub* hub, const int* fib, int 
         batch_fn fn = batch_kernel(m, nb, k >= 2);
         if (!fn) return bh_fail(parent, BH_ERR_UNSUPPORTED, "batched H.v: unsupported chain length");
         {
-            BhProfScope prof(parent, nb == 8 ? BH_PROF_HV_BATCH8 : nb == 4 ? BH_PROF_HV_BATCH4 : BH_PROF_HV_BATCH2, 16.0 * (double)D * nb);
+            BhProfScope prof(parent, nb == 4 ? BH_PROF_HV_BATCH4 : BH_PROF_HV_BATCH2, 16.0 * (double)D * nb);
             fn<<<grid, 256, 0, parent->stream>>>(parent->d_tab, D, parent->d_states, parent->d_dU, a);
         }
         BH_LAUNCHED(parent);
@@ -287,7 +271,7 @@ static int launch_group(bh_ctx* parent, bh_batch_hub* hub, const int* grp, int n
 {
     int pos = 0, rc = BH_OK;
     while (ng - pos >= 2 && rc == BH_OK) {
-        const int nb = (ng - pos >= 8) ? 8 : (ng - pos >= 4) ? 4 : 2;
+        const int nb = (ng - pos >= 4) ? 4 : 2;
         rc = apply_filters(parent, hub, grp + pos, nb);
         pos += nb;
     }
@@ -382,7 +366,7 @@ int bh_points_lockstep(bh_ctx* ctx, int nb, int64_t npoints, const double* cJ, c
     const auto t_children = std::chrono::steady_clock::now();
     bh_batch_hub* hub = ctx->hub;
     hub->sched.reset(nb);
-    int rcs[BH_MAX_BATCH] = {};
+    int rcs[BH_MAX_BATCH] = {BH_OK, BH_OK, BH_OK, BH_OK};
     int64_t next_point = 0;  // guarded by the baton (only the running fiber touches it)
     bool stop = false;
     std::vector<std::thread> threads;

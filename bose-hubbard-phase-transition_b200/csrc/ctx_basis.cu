@@ -58,7 +58,7 @@ extern "C" int bh_ctx_create(int device, bh_ctx** out)
         return bh_fail(nullptr, BH_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     ctx->own_stream = true;
-    if (const char* v = getenv("BH_BATCH")) ctx->batch = std::min(8, std::max(1, atoi(v)));
+    if (const char* v = getenv("BH_BATCH")) ctx->batch = std::min(4, std::max(1, atoi(v)));
     if (const char* v = getenv("BH_BATCH_PLAIN")) ctx->batch_plain = atoi(v);
     if (const char* v = getenv("BH_SELL_SIGMA")) ctx->sell_sigma = std::min(1024, std::max(32, atoi(v) / 32 * 32));
     if (const char* v = getenv("BH_COOP")) ctx->coop = atoi(v);
@@ -238,7 +238,7 @@ extern "C" int bh_ctx_set_stream(bh_ctx* ctx, void* cuda_stream)
 extern "C" int bh_ctx_set_batch(bh_ctx* ctx, int batch)
 {
     if (!ctx) return BH_ERR_ARG;
-    if (batch < 1 || batch > 8) return bh_fail(ctx, BH_ERR_ARG, "bh_ctx_set_batch: batch must be 1..8");
+    if (batch < 1 || batch > 4) return bh_fail(ctx, BH_ERR_ARG, "bh_ctx_set_batch: batch must be 1..4");
     ctx->batch = batch;
     return BH_OK;
 }

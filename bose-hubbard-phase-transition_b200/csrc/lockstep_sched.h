@@ -16,17 +16,17 @@
 #include <condition_variable>
 #include <mutex>
 
-#define LS_MAX_FIBERS 8
+#define LS_MAX_FIBERS 4
 
 struct LockstepSched {
     std::mutex mu;
     std::condition_variable cv;
     int nfib = 0;
     int turn = -1;  // fiber allowed to run; -1 when everybody has finished
-    bool done[LS_MAX_FIBERS] = {};
-    bool parked[LS_MAX_FIBERS] = {};
-    int key[LS_MAX_FIBERS] = {};
-    int rc[LS_MAX_FIBERS] = {};
+    bool done[LS_MAX_FIBERS] = {false, false, false, false};
+    bool parked[LS_MAX_FIBERS] = {false, false, false, false};
+    int key[LS_MAX_FIBERS] = {0, 0, 0, 0};
+    int rc[LS_MAX_FIBERS] = {0, 0, 0, 0};
 
     void reset(int n)
     {

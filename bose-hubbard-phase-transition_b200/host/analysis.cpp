@@ -77,7 +77,7 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
     std::vector<bh_ctx*> ctxs(nworkers, nullptr);
     for (int d = 0; d < nworkers; ++d) {
         if (bh_ctx_create(d % ngpu, &ctxs[d]) != BH_OK) throw std::runtime_error(bh_last_error(nullptr));
-        bh_ctx_set_batch(ctxs[d], std::max(1, std::min(8, opt.batch)));
+        bh_ctx_set_batch(ctxs[d], std::max(1, std::min(4, opt.batch)));
         if (bh_setup(ctxs[d], m, n, nbr_ptr.data(), nbr_idx.data()) != BH_OK) {
             std::string msg = bh_last_error(ctxs[d]);
             for (bh_ctx* c : ctxs) bh_ctx_destroy(c);
@@ -146,13 +146,13 @@ std::vector<Analysis::SweepPoint> calculate_and_save(int m, int n, const std::ve
         std::atomic<int> next(0), done(0);
         auto worker = [&](int d) {
             try {
-                const int B = std::max(1, std::min(8, opt.batch));
+                const int B = std::max(1, std::min(4, opt.batch));
                 int64_t dim = 0;
                 bh_dimension(m, n, &dim);
                 // a chunk of tasks per call: bh_points keeps B solves in lockstep (shared H.v launches, same results) and
                 // refills a finished solve from the chunk; small systems (D <= 100 000) are solved one CTA per grid point,
                 // so they are handed over in chunks large enough to fill the SMs of the GPU
-                const int chunk = B > 1 ? ((dim <= 100000 && kernel == BH_HV_MATRIX_FREE) ? 160 : std::max(16, 4 * B)) : 1;
+                const int chunk = B > 1 ? ((dim <= 100000 && kernel == BH_HV_MATRIX_FREE) ? 160 : std::min(16, 4 * B)) : 1;
                 std::vector<int> ts(chunk);
                 std::vector<double> cJ(chunk), cU(chunk), cmu(chunk), p1s(chunk), out3(3 * (size_t)chunk);
                 for (;;) {

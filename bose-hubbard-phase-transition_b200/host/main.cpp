@@ -36,7 +36,7 @@ static void print_usage()
               << "  -c, --concurrent Grid points solved concurrently per GPU (default 1)\n"
               << "      --no-plot   Do not run plot.py afterwards\n"
               << "      --resume    Checkpoint finished points in <output>.partial and skip them when restarted\n"
-              << "      --batch N   Grid points solved in lockstep per GPU, sharing their H.v launches (1..8, default 4)\n"
+              << "      --batch N   Grid points solved in lockstep per GPU, sharing their H.v launches (1..4, default 4)\n"
               << "      --reuse-shift  -f J / -f U: the chemical potential only shifts the spectrum; solve each row once\n";
 }
 
@@ -88,7 +88,7 @@ int main(int argc, char* argv[])
             case 1000: plot = false; break;
             case 1001: opt.reuse_shift = true; break;
             case 1002: opt.resume = true; break;
-            case 1003: opt.batch = std::max(1, std::min(8, std::atoi(optarg))); break;
+            case 1003: opt.batch = std::max(1, std::min(4, std::atoi(optarg))); break;
             case 'h':
             default: print_usage(); return 0;
         }

@@ -142,7 +142,7 @@ int bh_point(bh_ctx* ctx, double cJ, double cU, double cmu, int nb_eigen, int ke
 int bh_points(bh_ctx* ctx, const double* cJ, const double* cU, const double* cmu, int64_t npoints, int nb_eigen,
               int kernel, double* out3, bh_eigs_info* infos /* may be NULL */);
 /* Lockstep batching of bh_points (the independent iterations of the reference's `omp parallel for` over grid points,
- * src/analysis.cpp:302): with batch = 2..8, groups of that many points are solved together and share their H.v
+ * src/analysis.cpp:302): with batch = 2..4, groups of that many points are solved together and share their H.v
  * launches (closed chains, kernel = BH_HV_MATRIX_FREE; anything else falls back to one point at a time).
  * Results are the same point by point.  Default 1, or the environment variable BH_BATCH. */
 int bh_ctx_set_batch(bh_ctx* ctx, int batch);
@@ -165,10 +165,10 @@ int bh_partition(const bh_ctx* ctx, int64_t* row0, int64_t* nrows, int64_t* slic
  * With profiling enabled every launch of the classes below is bracketed by a pair of CUDA events on the context's
  * stream (the launching stream); bh_ctx_profile_read synchronises, adds up launches / milliseconds / algorithmic
  * bytes per class since the last read and clears the records.  Off by default (two event records per launch). */
-enum { BH_PROF_HV_FREE = 0 /* matrix-free H.v, one vector */, BH_PROF_HV_BATCH2 = 1, BH_PROF_HV_BATCH4 = 2 /* lockstep H.v */, BH_PROF_HV_BATCH8 = 9,
+enum { BH_PROF_HV_FREE = 0 /* matrix-free H.v, one vector */, BH_PROF_HV_BATCH2 = 1, BH_PROF_HV_BATCH4 = 2 /* lockstep H.v */,
        BH_PROF_HV_STORED = 3, BH_PROF_STEP = 4 /* Lanczos step after the H.v: three-term update + re-orthogonalisation */,
        BH_PROF_RESTART = 5 /* V <- V Y */, BH_PROF_GRAM = 6, BH_PROF_SPDM = 7, BH_PROF_SMALL = 8 /* many-point small-system steps */,
-       BH_PROF_NCLASSES = 10 };
+       BH_PROF_NCLASSES = 9 };
 int bh_ctx_profile_enable(bh_ctx* ctx, int on);
 int bh_ctx_profile_read(bh_ctx* ctx, int cls, int64_t* launches, double* total_ms, double* total_bytes);
 
