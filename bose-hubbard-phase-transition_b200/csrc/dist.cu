@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "bh_internal.h"
+#include "halo_plan.h"
 
 namespace {
 struct NcclApi {
@@ -161,7 +162,6 @@ int bh_dist_allgather(bh_ctx* ctx, const double* send, double* recv, int64_t cou
 // straight from the caller's local vector into d_xfull at their global offsets, while the context's stream computes the
 // hops whose source is local (k_hv_free_chain_part<.., 1>); the remote hops follow once the exchange has completed.
 // ---------------------------------------------------------------------------------------------------------
-#define HALO_CHUNK 4096
 
 int bh_dist_plan_halo(bh_ctx* ctx)
 {
@@ -194,32 +194,12 @@ int bh_dist_plan_halo(bh_ctx* ctx)
     BH_D2H(ctx, flags.data(), d_flags, flags.size());
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_flags);
-    // ranges of rank `owner`'s slice that rank `reader` reads: runs of flagged chunks clipped to the owner's slice;
-    // runs separated by fewer than 8 clean chunks are merged (fewer, larger messages)
-    auto ranges = [&](int reader, int owner, std::vector<bh_ctx::HaloRange>& out, int peer) {
-        const int64_t lo = per * owner, hi = std::min<int64_t>(ctx->D, per * (owner + 1));
-        if (hi <= lo) return;
-        const unsigned char* f = flags.data() + (size_t)reader * nchunks;
-        const int64_t c0 = lo / HALO_CHUNK, c1 = (hi + HALO_CHUNK - 1) / HALO_CHUNK;
-        int64_t run0 = -1, last = -1;
-        auto flush = [&]() {
-            if (run0 < 0) return;
-            const int64_t a = std::max(lo, run0 * HALO_CHUNK), b = std::min(hi, (last + 1) * HALO_CHUNK);
-            if (b > a) out.push_back({peer, a, b - a});
-            run0 = -1;
-        };
-        for (int64_t c = c0; c < c1; ++c) {
-            if (!f[c]) continue;
-            if (run0 >= 0 && c - last > 8) flush();
-            if (run0 < 0) run0 = c;
-            last = c;
-        }
-        flush();
-    };
-    for (int p = 0; p < W; ++p) {
-        if (p == ctx->rank) continue;
-        ranges(ctx->rank, p, ctx->halo_recv, p);  // what I read from p's slice
-        ranges(p, ctx->rank, ctx->halo_send, p);  // what p reads from mine
+    // what this rank receives from / sends to every peer (halo_plan.h: host-only, tested on the CPU)
+    {
+        std::vector<BhHaloRange> recv, send;
+        bh_halo_plan(flags.data(), nchunks, W, ctx->rank, per, ctx->D, 8, recv, send);
+        for (const auto& r : recv) ctx->halo_recv.push_back({r.peer, r.off, r.count});
+        for (const auto& r : send) ctx->halo_send.push_back({r.peer, r.off, r.count});
     }
     ctx->halo_recv_elems = 0;
     for (const auto& r : ctx->halo_recv) ctx->halo_recv_elems += r.count;

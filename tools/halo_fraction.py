@@ -1,56 +1,50 @@
-"""CPU (numpy): remote elements a rank needs for one H.v under two static row partitions of the closed chain -- a contiguous LEX
-slice, and a contiguous suffix-rank range of every sector of the split layout (hv_split_tables.h) -- as a fraction of D.
-usage: halo_fraction.py m   (n = m, cut p = m // 2, W = 2, 4, 8).  Numbers quoted in DESIGN.md section 9."""
-import numpy as np, sys
-from math import comb
-def gen(m,n):
-    if m==1: return np.array([[n]],dtype=np.int8)
-    blocks=[]
-    for k in range(n,-1,-1):
-        sub=gen(m-1,n-k)
-        blocks.append(np.hstack([np.full((len(sub),1),k,dtype=np.int8),sub]))
-    return np.vstack(blocks)
-m=int(sys.argv[1]); n=m; p=m//2; s=m-p
-f=np.zeros((m,n+2),dtype=np.int64)
-for q in range(m-1):
-    for R in range(1,n+2): f[q][R]=comb(R-1+m-1-q,m-1-q)
-def rank(S):
-    after=n-np.cumsum(S.astype(np.int64),axis=1)
-    r=np.zeros(len(S),dtype=np.int64)
-    for q in range(m-1): r+=f[q][after[:,q]]
-    return r
-def sufinfo(S):
-    after=n-np.cumsum(S.astype(np.int64),axis=1)
-    R=after[:,p-1]
-    sr=np.zeros(len(S),dtype=np.int64)
-    for q in range(p,m-1): sr+=f[q][after[:,q]]
-    return R,sr
-S=gen(m,n); D=len(S)
-R,sr=sufinfo(S)
-nS=np.array([comb(r+s-1,s-1) for r in range(n+1)])
-for W in (2,4,8):
-    # owner by suffix range within the sector (even split of sufrank range)
-    own=(sr*W)//nS[R]
-    # owner by contiguous LEX slice
-    nloc=(D+W-1)//W
-    own_lex=np.arange(D)//nloc
-    res={}
-    for name,ow in (("suffix-range",own),("LEX-slice",own_lex)):
-        need=[set() for _ in range(W)]
-        cnt=np.zeros(W)
-        needmask=np.zeros((W,D),dtype=bool)
-        for q in range(m):
-            a,b=q,(q+1)%m
-            for (src,dst) in ((a,b),(b,a)):
-                ok=S[:,src]>0
-                rows=np.nonzero(ok)[0]
-                T=S[ok].copy(); T[:,src]-=1; T[:,dst]+=1
-                t=rank(T)
-                remote=ow[rows]!=ow[t]
-                for r in range(W):
-                    sel=remote&(ow[rows]==r)
-                    needmask[r,t[sel]]=True
-        fr=needmask.sum(axis=1)/D
-        sizes=np.bincount(ow,minlength=W)/D
-        res[name]=(fr,sizes)
-        print(m,W,name,"remote elements needed / D per rank:",np.round(fr,3),"max",round(fr.max(),3),"own share",np.round(sizes,3))
+#!/usr/bin/env python3
+"""Hop-graph analysis of the row partition (CPU, numpy): for W contiguous LEX slices of a closed chain, the fraction of D that a
+rank reads from the other slices, the remote hops per row, and how the halo splits over P consecutive row pieces of a slice (the
+numbers quoted in DESIGN.md section 7).
+
+    python tools/halo_fraction.py M W [P]
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as O  # noqa: E402
+from test_halo_plan import lex_rank  # noqa: E402
+
+m = n = int(sys.argv[1])
+W = int(sys.argv[2])
+P = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+_, bas = O.basis(m, n, O.LEX)
+bas = bas.astype(np.int64)
+D = len(bas)
+per = -(-D // W)
+CH = max(1, D // 2000)
+for r in range(W):
+    lo, hi = r * per, min(D, (r + 1) * per)
+    S = bas[lo:hi]
+    piece = (np.arange(hi - lo) * P) // (hi - lo)
+    need = [set() for _ in range(P)]
+    rem_hops = 0
+    for q in range(m):
+        a, b = q, (q + 1) % m
+        for src, dst in ((a, b), (b, a)):
+            ok = S[:, src] > 0
+            T = S[ok].copy()
+            T[:, src] -= 1
+            T[:, dst] += 1
+            t = lex_rank(T, n)
+            remote = (t < lo) | (t >= hi)
+            rem_hops += remote.sum()
+            pc, ch = piece[ok][remote], t[remote] // CH
+            for p in range(P):
+                need[p].update(np.unique(ch[pc == p]).tolist())
+    seen, inc = set(), []
+    for p in range(P):
+        inc.append(len(need[p] - seen))
+        seen |= need[p]
+    print(f"rank {r}/{W}: rows {hi - lo}, remote hops per row {rem_hops / (hi - lo):.2f}, halo {len(seen) * CH / D:.3f} D "
+          f"(all-gather: {(W - 1) / W:.3f} D); new chunks per row piece {inc}")
