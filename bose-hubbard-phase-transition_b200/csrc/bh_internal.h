@@ -83,6 +83,15 @@ struct bh_ctx {
     cudaEvent_t ev_x_ready = nullptr, ev_halo_done = nullptr;
     bool halo_ready = false;
     int64_t halo_recv_elems = 0;
+    // peer-memory form (dist.cu, default for chains): every vector that can be the input of an H.v (Krylov basis, w, f, the three
+    // Chebyshev buffers) lives in ONE arena per rank, exported with CUDA IPC; a rank's sweep loads the source elements that live in
+    // another slice straight from that rank's arena over NVLink (coalesced: a hop shifts 32 consecutive rows to 32 consecutive
+    // elements), after a barrier that orders it behind the kernels that produced the vector.  No exchange, no second pass.
+    double* d_arena = nullptr;
+    int arena_ncv = 0;
+    std::vector<void*> peer_arena;   // [world]; own entry = d_arena
+    bool peer_ready = false;
+    double* d_barrier = nullptr;
     // the hops of this rank's rows whose source element lives in another rank's slice, stored once as a CSR matrix
     // (pattern and amplitudes are fixed by the basis and the partition; 2J is applied at run time)
     int* d_rem_ptr = nullptr;     // [nloc + 1]
@@ -250,6 +259,18 @@ int bh_dist_plan_halo(bh_ctx* ctx);                              // once per bh_
 int bh_dist_halo_begin(bh_ctx* ctx, const double* x_local);      // start the exchange of x into d_xfull (communication stream)
 int bh_dist_halo_end(bh_ctx* ctx);                               // the context's stream waits for it
 void bh_dist_release_halo(bh_ctx* ctx);
+bool bh_dist_peer_wanted(const bh_ctx* ctx);                     // partitioned chain context with the peer-memory form enabled
+int bh_dist_arena(bh_ctx* ctx, int ncv);                         // (re)allocate + export + open the vector arenas (collective)
+void bh_dist_arena_release(bh_ctx* ctx);
+int bh_dist_barrier(bh_ctx* ctx);                                // all ranks' prior work on their context streams is complete
+// view of the arenas handed to the peer-memory H.v kernel
+struct BhPeerView {
+    const double* base[8];  // arena of every rank (device pointers valid on this device)
+    int64_t per;            // slice length
+    int64_t x_off;          // offset of the input vector inside an arena (the same on every rank)
+    float inv_per;
+    int world;
+};
 
 // host-side small dense symmetric eigen-decomposition (ascending; vectors in columns of v, column-major)
 void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::vector<double>& v);

@@ -83,6 +83,7 @@ static void free_dev(void* p)
 void bh_release_workspace(bh_ctx* ctx)
 {
     if (!ctx->parent) bh_small_release(ctx);  // lockstep children alias the pointer of their parent
+    if (ctx->d_arena) bh_dist_arena_release(ctx);  // partitioned context: V, w, f, cheb live in one exported arena
     free_dev(ctx->d_V); ctx->d_V = nullptr;
     free_dev(ctx->d_w); ctx->d_w = nullptr;
     free_dev(ctx->d_f); ctx->d_f = nullptr;

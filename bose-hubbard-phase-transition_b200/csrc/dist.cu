@@ -102,9 +102,125 @@ void bh_dist_release_halo(bh_ctx* ctx)
     ctx->halo_recv_elems = 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Peer-memory form of the partitioned H.v: one arena per rank, exported with CUDA IPC and mapped by every other rank
+// ---------------------------------------------------------------------------------------------------------
+bool bh_dist_peer_wanted(const bh_ctx* ctx)
+{
+    static const int enabled = getenv("BH_DIST_PEER") ? atoi(getenv("BH_DIST_PEER")) : 1;
+    return enabled && ctx->partitioned && ctx->world > 1 && ctx->world <= 8 && ctx->h_tab.chain && ctx->m >= 3 && !getenv("BH_DIST_ALLGATHER");
+}
+
+void bh_dist_arena_release(bh_ctx* ctx)
+{
+    if (!ctx->d_arena) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (int p = 0; p < (int)ctx->peer_arena.size(); ++p)
+        if (p != ctx->rank && ctx->peer_arena[p]) cudaIpcCloseMemHandle(ctx->peer_arena[p]);
+    ctx->peer_arena.clear();
+    ctx->peer_ready = false;
+    // every rank has unmapped the others' arenas before any arena is freed
+    if (ctx->nccl_comm && ctx->d_barrier) {
+        g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(ctx->d_arena);
+    ctx->d_arena = nullptr;
+    ctx->arena_ncv = 0;
+    ctx->d_V = ctx->d_w = ctx->d_f = nullptr;
+    for (int q = 0; q < 3; ++q) ctx->d_cheb[q] = nullptr;
+    ctx->ws_ncv = 0;
+}
+
+// Arena layout (doubles): V (ncv + 1) ld | w ld | f ld | cheb0 ld | cheb1 ld | cheb2 ld.  Collective: every rank calls it with
+// the same ncv at the same point of the solve.  Growing keeps w, f and the Chebyshev buffers (not the basis, like the
+// ordinary workspace).
+int bh_dist_arena(bh_ctx* ctx, int ncv)
+{
+    if (ctx->d_arena && ncv <= ctx->arena_ncv) return BH_OK;
+    BH_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = ctx->world;
+    const int64_t ld = ctx->ld;
+    const size_t ndoubles = (size_t)ld * (ncv + 1 + 5);
+    double* fresh = nullptr;
+    BH_CUDA(ctx, cudaMalloc(&fresh, sizeof(double) * ndoubles));
+    BH_CUDA(ctx, cudaMemsetAsync(fresh, 0, sizeof(double) * ndoubles, ctx->stream));
+    double* nw = fresh + (size_t)ld * (ncv + 1);
+    if (ctx->d_arena) {  // keep the small vectors (pointer roles may have been swapped: copy by role)
+        BH_CUDA(ctx, cudaMemcpyAsync(nw, ctx->d_w, sizeof(double) * ld, cudaMemcpyDeviceToDevice, ctx->stream));
+        BH_CUDA(ctx, cudaMemcpyAsync(nw + ld, ctx->d_f, sizeof(double) * ld, cudaMemcpyDeviceToDevice, ctx->stream));
+        for (int q = 0; q < 3; ++q)
+            BH_CUDA(ctx, cudaMemcpyAsync(nw + (2 + q) * ld, ctx->d_cheb[q], sizeof(double) * ld, cudaMemcpyDeviceToDevice, ctx->stream));
+        BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        bh_dist_arena_release(ctx);
+    }
+    if (!ctx->d_barrier) {
+        BH_CUDA(ctx, cudaMalloc(&ctx->d_barrier, sizeof(double) * 2));
+        BH_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, sizeof(double) * 2, ctx->stream));
+    }
+    ctx->d_arena = fresh;
+    ctx->arena_ncv = ncv;
+    ctx->d_V = fresh;
+    ctx->d_w = nw;
+    ctx->d_f = nw + ld;
+    for (int q = 0; q < 3; ++q) ctx->d_cheb[q] = nw + (2 + q) * ld;
+    ctx->ws_ncv = ncv;
+    // export my arena, gather everybody's handle, map the others
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t mine;
+    ctx->peer_ready = false;
+    ctx->peer_arena.assign(W, nullptr);
+    ctx->peer_arena[ctx->rank] = fresh;
+    const bool exported = cudaIpcGetMemHandle(&mine, fresh) == cudaSuccess;
+    if (!exported) {
+        cudaGetLastError();
+        std::memset(&mine, 0, sizeof(mine));
+    }
+    unsigned char* d_h = nullptr;
+    BH_CUDA(ctx, cudaMalloc(&d_h, 64 * (size_t)W + 8));
+    BH_CUDA(ctx, cudaMemcpyAsync(d_h + 64 * (size_t)ctx->rank, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    BH_NCCL(ctx, g_nccl.AllGather(d_h + 64 * (size_t)ctx->rank, d_h, 64, ncclUint8, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all(W);
+    BH_CUDA(ctx, cudaMemcpyAsync(all.data(), d_h, 64 * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_h);
+    bool ok = exported;
+    for (int p = 0; p < W && ok; ++p) {
+        if (p == ctx->rank) continue;
+        bool zero = true;
+        for (size_t b = 0; b < 64; ++b) zero = zero && reinterpret_cast<const unsigned char*>(&all[p])[b] == 0;
+        void* ptr = nullptr;
+        if (zero || cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+            break;
+        }
+        ctx->peer_arena[p] = ptr;
+    }
+    // the form is used only if EVERY rank could map every arena (one all-reduce of a flag; also the first barrier)
+    double flag = ok ? 0.0 : 1.0;
+    BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_barrier + 1, &flag, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BH_NCCL(ctx, g_nccl.AllReduce(ctx->d_barrier + 1, ctx->d_barrier + 1, 1, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));
+    BH_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_barrier + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->peer_ready = (flag == 0.0);
+    if (getenv("BH_DIST_VERBOSE"))
+        fprintf(stderr, "[bh] rank %d arena %.1f MB (ncv %d): peer-memory H.v %s\n", ctx->rank, ndoubles * 8e-6, ncv,
+                ctx->peer_ready ? "enabled" : "NOT available (CUDA IPC failed on some rank): halo exchange form");
+    return BH_OK;
+}
+
+int bh_dist_barrier(bh_ctx* ctx)
+{
+    BH_NCCL(ctx, g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));
+    return BH_OK;
+}
+
 extern "C" int bh_dist_finalize(bh_ctx* ctx)
 {
     if (!ctx) return BH_ERR_ARG;
+    bh_dist_arena_release(ctx);
+    if (ctx->d_barrier) { cudaFree(ctx->d_barrier); ctx->d_barrier = nullptr; }
     bh_dist_release_halo(ctx);
     if (ctx->comm_stream) {
         cudaStreamSynchronize(ctx->comm_stream);

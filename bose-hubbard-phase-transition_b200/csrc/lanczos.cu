@@ -812,6 +812,8 @@ __global__ void k_gram_reduce(int nparts, const double* __restrict__ part, int n
 int bh_ensure_workspace(bh_ctx* ctx, int ncv)
 {
     if (!ctx->D) return bh_fail(ctx, BH_ERR_STATE, "no system: call bh_setup first");
+    // row-partitioned chain context: basis, w, f and the Chebyshev buffers live in one arena that the other ranks map (dist.cu)
+    if (bh_dist_peer_wanted(ctx)) BH_TRY(bh_dist_arena(ctx, std::max(ncv, 12)));
     // vectors are padded to ld (a multiple of 32) with zeros: the re-orthogonalisation kernels read row pairs
     if (!ctx->d_w) {
         BH_CUDA(ctx, cudaMalloc(&ctx->d_w, sizeof(double) * ctx->ld));
@@ -1270,6 +1272,7 @@ int bh_lanczos(bh_ctx* ctx, double cJ, double cU, double cmu, int nev, int ncv, 
 {
     const auto t_start = std::chrono::steady_clock::now();
     int hv_count = 0;
+    BH_TRY(bh_ensure_workspace(ctx, std::min(ncv, BH_MAX_NCV)));  // full size up front: no reallocation between the stages
     LanczosOp plain = [&](const double* x, double* y) {
         ++hv_count;
         if (ctx->parent && ctx->parent->hub && ctx->parent->batch_plain) {
