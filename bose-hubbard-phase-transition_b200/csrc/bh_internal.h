@@ -84,9 +84,9 @@ struct bh_ctx {
     bool halo_ready = false;
     int64_t halo_recv_elems = 0;
     // peer-memory form (dist.cu, default for chains): every vector that can be the input of an H.v (Krylov basis, w, f, the three
-    // Chebyshev buffers) lives in ONE arena per rank, exported with CUDA IPC; a rank's sweep loads the source elements that live in
-    // another slice straight from that rank's arena over NVLink (coalesced: a hop shifts 32 consecutive rows to 32 consecutive
-    // elements), after a barrier that orders it behind the kernels that produced the vector.  No exchange, no second pass.
+    // Chebyshev buffers) lives in ONE arena per rank, exported with CUDA IPC and mapped by every other rank; after a barrier the
+    // copy engines pull the ranges of the halo plan straight out of the owners' arenas over NVLink while the SMs sweep the
+    // local hops.
     double* d_arena = nullptr;
     int arena_ncv = 0;
     std::vector<void*> peer_arena;   // [world]; own entry = d_arena
@@ -263,14 +263,7 @@ bool bh_dist_peer_wanted(const bh_ctx* ctx);                     // partitioned 
 int bh_dist_arena(bh_ctx* ctx, int ncv);                         // (re)allocate + export + open the vector arenas (collective)
 void bh_dist_arena_release(bh_ctx* ctx);
 int bh_dist_barrier(bh_ctx* ctx);                                // all ranks' prior work on their context streams is complete
-// view of the arenas handed to the peer-memory H.v kernel
-struct BhPeerView {
-    const double* base[8];  // arena of every rank (device pointers valid on this device)
-    int64_t per;            // slice length
-    int64_t x_off;          // offset of the input vector inside an arena (the same on every rank)
-    float inv_per;
-    int world;
-};
+int bh_dist_pull_begin(bh_ctx* ctx, int64_t x_off);             // copy-engine pulls of the halo ranges out of the peers' arenas
 
 // host-side small dense symmetric eigen-decomposition (ascending; vectors in columns of v, column-major)
 void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::vector<double>& v);

@@ -210,6 +210,20 @@ int bh_dist_arena(bh_ctx* ctx, int ncv)
     return BH_OK;
 }
 
+// Copy-engine pulls of this rank's halo ranges out of the peers' arenas (x lives at offset x_off of every arena) into d_xfull,
+// on the communication stream, ordered after everything enqueued on the context's stream so far (the barrier included).
+int bh_dist_pull_begin(bh_ctx* ctx, int64_t x_off)
+{
+    BH_CUDA(ctx, cudaEventRecord(ctx->ev_x_ready, ctx->stream));
+    BH_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x_ready, 0));
+    for (const auto& r : ctx->halo_recv) {
+        const double* src = static_cast<const double*>(ctx->peer_arena[r.peer]) + x_off + (r.off - ctx->ld * r.peer);
+        BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_xfull + r.off, src, sizeof(double) * (size_t)r.count, cudaMemcpyDefault, ctx->comm_stream));
+    }
+    BH_CUDA(ctx, cudaEventRecord(ctx->ev_halo_done, ctx->comm_stream));
+    return BH_OK;
+}
+
 int bh_dist_barrier(bh_ctx* ctx)
 {
     BH_NCCL(ctx, g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream));

@@ -225,92 +225,6 @@ k_hv_free_chain_part(const BhTables* __restrict__ gtab, int64_t row0, int64_t D,
     }
 }
 
-// Peer-memory form of the partitioned chain kernel: the ordinary single sweep, but a source element that lives in another
-// rank's slice is loaded straight from that rank's arena over NVLink (BhPeerView: every rank keeps its vectors at the same
-// offsets of an arena the others have mapped with CUDA IPC).  A hop shifts 32 consecutive rows to 32 consecutive elements, so
-// the remote loads of a warp coalesce into a few 128-byte NVLink requests; about one hop per row is remote at 2 ranks.
-template <int M, bool CLOSED>
-__global__ void __launch_bounds__(256, CHAIN_MIN_BLOCKS)
-k_hv_free_chain_peer(const BhTables* __restrict__ gtab, int64_t row0, int64_t D, const uint64_t* __restrict__ states,
-                     const double* __restrict__ dU, double cJ, double cU, double cmu, const __grid_constant__ BhPeerView pv,
-                     const double* __restrict__ x /* local slice */, double* __restrict__ y, BhEpilogue ep)
-{
-    __shared__ BhTables t;
-    bh_stage_tables(&t, gtab);
-    const double shift = __dmul_rn(-(double)t.n, cmu);
-    const unsigned lo = (unsigned)row0, len = (unsigned)D;
-    const double* xl = x - row0;  // local slice addressed by global rank
-    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < D; l += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k = row0 + l;
-        const uint64_t s = states[l];
-        const int kk = (int)k;
-        const int n0 = bh_occ(s, 0);
-        int R = t.n - n0, nprev = n0, tdn = 0, tup = 0;
-        double acc = 0.0;
-        auto hop = [&](int cond, int tgt, double amp) {
-            double xv = 0.0;
-            if (cond) {
-                if (((unsigned)tgt - lo) < len) {
-                    xv = __ldg(xl + tgt);
-                } else {
-                    int owner = (int)((float)tgt * pv.inv_per);             // estimate, exact after one correction step
-                    owner = min(max(owner, 0), pv.world - 1);
-                    if ((int64_t)tgt < (int64_t)owner * pv.per) --owner;
-                    else if ((int64_t)tgt >= (int64_t)(owner + 1) * pv.per) ++owner;
-                    xv = pv.base[owner][pv.x_off + ((int64_t)tgt - (int64_t)owner * pv.per)];
-                }
-            }
-            acc = fma(amp, xv, acc);
-        };
-#pragma unroll
-        for (int q = 0; q < M - 1; ++q) {
-            const int nnext = bh_occ(s, q + 1);
-            const int2 gh = t.gh[q][R];
-            hop(nnext, kk + gh.x, t.sq[(nprev + 1) * nnext]);
-            hop(nprev, kk + gh.y, t.sq[(nnext + 1) * nprev]);
-            tdn += gh.x;
-            tup += gh.y;
-            R -= nnext;
-            nprev = nnext;
-        }
-        if (CLOSED) {
-            const int nl = nprev;
-            hop(nl, kk + tdn, t.sq[(n0 + 1) * nl]);
-            hop(n0, kk + tup, t.sq[(nl + 1) * n0]);
-        }
-        const double diag = __dadd_rn(__dmul_rn(dU[l], cU), shift);
-        const double xv = x[l];
-        double out = ep.s1 * (diag * xv - (2.0 * cJ) * acc);
-        if (ep.s2 != 0.0) out = fma(ep.s2, xv, out);
-        if (ep.z) out = fma(ep.s3, ep.z[l], out);
-        y[l] = out;
-    }
-}
-
-typedef void (*hv_peer_fn_t)(const BhTables*, int64_t, int64_t, const uint64_t*, const double*, double, double, double, const BhPeerView,
-                             const double*, double*, BhEpilogue);
-template <bool CLOSED>
-static hv_peer_fn_t hv_chain_peer_kernel(int m)
-{
-    switch (m) {
-        case 3: return k_hv_free_chain_peer<3, CLOSED>;
-        case 4: return k_hv_free_chain_peer<4, CLOSED>;
-        case 5: return k_hv_free_chain_peer<5, CLOSED>;
-        case 6: return k_hv_free_chain_peer<6, CLOSED>;
-        case 7: return k_hv_free_chain_peer<7, CLOSED>;
-        case 8: return k_hv_free_chain_peer<8, CLOSED>;
-        case 9: return k_hv_free_chain_peer<9, CLOSED>;
-        case 10: return k_hv_free_chain_peer<10, CLOSED>;
-        case 11: return k_hv_free_chain_peer<11, CLOSED>;
-        case 12: return k_hv_free_chain_peer<12, CLOSED>;
-        case 13: return k_hv_free_chain_peer<13, CLOSED>;
-        case 14: return k_hv_free_chain_peer<14, CLOSED>;
-        case 15: return k_hv_free_chain_peer<15, CLOSED>;
-        case 16: return k_hv_free_chain_peer<16, CLOSED>;
-    }
-    return nullptr;
-}
-
 // Which 4096-row chunks of the global vector hold a source element of some hop of this rank's rows: flags[chunk] = 1
 // (the halo plan of dist.cu is built from these flags once per bh_setup_partitioned).
 #define HALO_CHUNK_SHIFT 12
@@ -645,21 +559,27 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
         // row-partitioned context: x is the local slice; exchange it (NCCL all-gather) and read the full vector
         const double* xin = x;
         const int64_t nloc = ctx->nloc;
-        if (ctx->partitioned && ctx->peer_ready && ctx->d_arena && x >= ctx->d_arena &&
+        if (ctx->partitioned && ctx->peer_ready && ctx->halo_ready && ctx->d_arena && x >= ctx->d_arena &&
             x + ctx->ld <= ctx->d_arena + (size_t)ctx->ld * (ctx->arena_ncv + 1 + 5)) {
-            // peer-memory form: barrier (every rank has finished the kernels that wrote its part of x, and finished reading whatever
-            // y overwrites), then ONE sweep that loads remote source elements straight from the owners' arenas over NVLink
+            // Peer-memory form (default for chains): every rank keeps its vectors at the same offsets of an arena the others have
+            // mapped with CUDA IPC.  After a barrier (all ranks have finished the kernels that wrote their part of x) the copy
+            // engines PULL the ranges of the halo plan straight out of the owners' arenas over NVLink -- no NCCL kernel, no SM
+            // taken from the sweep -- while the SMs compute the hops whose source is local; the stored remote hops follow.
+            // (Loading the remote elements inside the sweep itself was measured slower: NVLink latency stalls a kernel that is
+            // already latency-bound, 0.36 s per solve against 0.29 s)
             BH_TRY(bh_dist_barrier(ctx));
+            BH_TRY(bh_dist_pull_begin(ctx, x - ctx->d_arena));
             if (nloc > 0) {
-                BhPeerView pv;
-                for (int p = 0; p < 8; ++p) pv.base[p] = (p < ctx->world) ? static_cast<const double*>(ctx->peer_arena[p]) : nullptr;
-                pv.per = ctx->ld;
-                pv.x_off = x - ctx->d_arena;
-                pv.inv_per = 1.0f / (float)ctx->ld;
-                pv.world = ctx->world;
-                hv_peer_fn_t fn = (ctx->h_tab.chain == 2) ? hv_chain_peer_kernel<true>(ctx->m) : hv_chain_peer_kernel<false>(ctx->m);
+                const bool closed = ctx->h_tab.chain == 2;
+                hv_free_fn_t f1 = closed ? hv_chain_part_kernel<true>(ctx->m) : hv_chain_part_kernel<false>(ctx->m);
                 const int grid = (int)std::min<int64_t>(nblocks(nloc, 256), (int64_t)ctx->sm_count * 8);
-                fn<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, pv, x, y, ep);
+                f1<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x - ctx->row0, y, ep);
+                BH_LAUNCHED(ctx);
+            }
+            BH_TRY(bh_dist_halo_end(ctx));
+            if (nloc > 0 && ctx->rem_nnz > 0) {
+                k_hv_remote<<<nblocks(nloc, 256), 256, 0, ctx->stream>>>(nloc, ctx->d_rem_ptr, ctx->d_rem_col, ctx->d_rem_amp, ctx->d_xfull, y,
+                                                                         ep.s1 * (-2.0 * cJ));
                 BH_LAUNCHED(ctx);
             }
             BH_CUDA(ctx, cudaGetLastError());
