@@ -92,6 +92,8 @@ struct bh_ctx {
     std::vector<void*> peer_arena;   // [world]; own entry = d_arena
     bool peer_ready = false;
     double* d_barrier = nullptr;
+    std::vector<cudaStream_t> pull_stream;  // one per peer: the pulls from different peers run on different copy engines
+    std::vector<cudaEvent_t> pull_done;
     // the hops of this rank's rows whose source element lives in another rank's slice, stored once as a CSR matrix
     // (pattern and amplitudes are fixed by the basis and the partition; 2J is applied at run time)
     int* d_rem_ptr = nullptr;     // [nloc + 1]
@@ -264,6 +266,7 @@ int bh_dist_arena(bh_ctx* ctx, int ncv);                         // (re)allocate
 void bh_dist_arena_release(bh_ctx* ctx);
 int bh_dist_barrier(bh_ctx* ctx);                                // all ranks' prior work on their context streams is complete
 int bh_dist_pull_begin(bh_ctx* ctx, int64_t x_off);             // copy-engine pulls of the halo ranges out of the peers' arenas
+int bh_dist_pull_end(bh_ctx* ctx);                               // the context's stream waits for them
 
 // host-side small dense symmetric eigen-decomposition (ascending; vectors in columns of v, column-major)
 void bh_sym_eig(int n, std::vector<double>& a, std::vector<double>& evals, std::vector<double>& v);

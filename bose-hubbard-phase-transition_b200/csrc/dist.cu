@@ -119,6 +119,12 @@ void bh_dist_arena_release(bh_ctx* ctx)
         if (p != ctx->rank && ctx->peer_arena[p]) cudaIpcCloseMemHandle(ctx->peer_arena[p]);
     ctx->peer_arena.clear();
     ctx->peer_ready = false;
+    for (cudaStream_t st : ctx->pull_stream)
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (cudaEvent_t e : ctx->pull_done)
+        if (e) cudaEventDestroy(e);
+    ctx->pull_stream.clear();
+    ctx->pull_done.clear();
     // every rank has unmapped the others' arenas before any arena is freed
     if (ctx->nccl_comm && ctx->d_barrier) {
         g_nccl.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream);
@@ -214,13 +220,40 @@ int bh_dist_arena(bh_ctx* ctx, int ncv)
 // on the communication stream, ordered after everything enqueued on the context's stream so far (the barrier included).
 int bh_dist_pull_begin(bh_ctx* ctx, int64_t x_off)
 {
-    BH_CUDA(ctx, cudaEventRecord(ctx->ev_x_ready, ctx->stream));
-    BH_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x_ready, 0));
-    for (const auto& r : ctx->halo_recv) {
-        const double* src = static_cast<const double*>(ctx->peer_arena[r.peer]) + x_off + (r.off - ctx->ld * r.peer);
-        BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_xfull + r.off, src, sizeof(double) * (size_t)r.count, cudaMemcpyDefault, ctx->comm_stream));
+    const int W = ctx->world;
+    if ((int)ctx->pull_stream.size() < W) {
+        int prio_lo = 0, prio_hi = 0;
+        BH_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        ctx->pull_stream.resize(W, nullptr);
+        ctx->pull_done.resize(W, nullptr);
+        for (int p = 0; p < W; ++p) {
+            if (p == ctx->rank) continue;
+            BH_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->pull_stream[p], cudaStreamNonBlocking, prio_hi));
+            BH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pull_done[p], cudaEventDisableTiming));
+        }
     }
-    BH_CUDA(ctx, cudaEventRecord(ctx->ev_halo_done, ctx->comm_stream));
+    BH_CUDA(ctx, cudaEventRecord(ctx->ev_x_ready, ctx->stream));
+    std::vector<char> used(W, 0);
+    for (const auto& r : ctx->halo_recv) {
+        if (!used[r.peer]) {
+            BH_CUDA(ctx, cudaStreamWaitEvent(ctx->pull_stream[r.peer], ctx->ev_x_ready, 0));
+            used[r.peer] = 1;
+        }
+        const double* src = static_cast<const double*>(ctx->peer_arena[r.peer]) + x_off + (r.off - ctx->ld * r.peer);
+        BH_CUDA(ctx, cudaMemcpyAsync(ctx->d_xfull + r.off, src, sizeof(double) * (size_t)r.count, cudaMemcpyDefault, ctx->pull_stream[r.peer]));
+    }
+    for (int p = 0; p < W; ++p)
+        if (used[p]) BH_CUDA(ctx, cudaEventRecord(ctx->pull_done[p], ctx->pull_stream[p]));
+    return BH_OK;
+}
+
+// the context's stream waits for the pulls of bh_dist_pull_begin
+int bh_dist_pull_end(bh_ctx* ctx)
+{
+    std::vector<char> used(ctx->world, 0);
+    for (const auto& r : ctx->halo_recv) used[r.peer] = 1;
+    for (int p = 0; p < ctx->world; ++p)
+        if (used[p]) BH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pull_done[p], 0));
     return BH_OK;
 }
 
@@ -337,7 +370,7 @@ int bh_dist_plan_halo(bh_ctx* ctx)
     BH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->halo_ready = true;
     if (getenv("BH_DIST_VERBOSE"))
-        fprintf(stderr, "[bh] rank %d halo plan: %zu recv ranges (%.1f MB = %.3f D), %zu send ranges, %.2f remote hops per row\n", ctx->rank,
+        fprintf(stderr, "[bh] rank %d of %d halo plan: %zu recv ranges (%.1f MB = %.3f D), %zu send ranges, %.2f remote hops per row\n", ctx->rank, W,
                 ctx->halo_recv.size(), ctx->halo_recv_elems * 8e-6, (double)ctx->halo_recv_elems / (double)ctx->D, ctx->halo_send.size(),
                 (double)ctx->rem_nnz / (double)std::max<int64_t>(ctx->nloc, 1));
     return BH_OK;

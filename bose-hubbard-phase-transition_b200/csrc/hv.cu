@@ -576,7 +576,7 @@ int bh_launch_hv(bh_ctx* ctx, double cJ, double cU, double cmu, int kernel_in, c
                 f1<<<grid, 256, 0, ctx->stream>>>(ctx->d_tab, ctx->row0, nloc, ctx->d_states, ctx->d_dU, cJ, cU, cmu, x - ctx->row0, y, ep);
                 BH_LAUNCHED(ctx);
             }
-            BH_TRY(bh_dist_halo_end(ctx));
+            BH_TRY(bh_dist_pull_end(ctx));
             if (nloc > 0 && ctx->rem_nnz > 0) {
                 k_hv_remote<<<nblocks(nloc, 256), 256, 0, ctx->stream>>>(nloc, ctx->d_rem_ptr, ctx->d_rem_col, ctx->d_rem_amp, ctx->d_xfull, y,
                                                                          ep.s1 * (-2.0 * cJ));
