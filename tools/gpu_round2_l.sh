@@ -14,7 +14,7 @@ run BH_HALO_GRID=4
 run BH_HALO_GRID=7 BH_HALO_ABLATE=5
 run BH_DIST_ALLGATHER=1
 fi
-( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29543 \
+( BH_DIST_VERBOSE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29543 \
     bench.py --gpus $NP --steps 3 --warmup 3 2> gpurun_out/l_bench_n$NP.err ) > gpurun_out/l_bench_n$NP.json
 python - <<PY
 import json
