@@ -103,3 +103,32 @@ def write_phase(path, grid, rows):
         f.write(f"{grid['fixed']} {fmt(grid['fixed_value'])}\n")
         for r in rows:
             f.write(" ".join(fmt(v) for v in r) + "\n")
+
+
+AXES = {"J": ("U", "mu"), "U": ("J", "mu"), "u": ("J", "U")}
+
+
+def read_phase(path):
+    """Reader side of the phase.txt contract (the reference's only consumer is plot.py:15-64).
+
+    Line 1: "<fixed parameter: J|U|u> <its value>"; then one row per grid point, "p1 p2 gap_ratio condensate_fraction
+    coherence", p1 outer / p2 inner (src/analysis.cpp:384-387).  Returns the header, the two axes and the three observable
+    grids indexed [i1, i2] in WRITING order (plot.py reshapes to (len(y), len(x)), which only agrees with this for square
+    grids).  An incomplete file (a sweep still running under --resume) yields NaN for the missing points.
+    """
+    import numpy as np
+    with open(path) as f:
+        head = f.readline().split()
+        if len(head) != 2 or head[0] not in AXES:
+            raise ValueError("Invalid fixed parameter in phase.txt")
+        rows = [[float(v) for v in line.split()] for line in f if line.strip()]
+    data = np.array(rows, dtype=float).reshape(-1, 5)
+    x = np.unique(data[:, 0])
+    y = np.unique(data[:, 1])
+    grids = np.full((3, len(x), len(y)), np.nan)
+    ix = np.searchsorted(x, data[:, 0])
+    iy = np.searchsorted(y, data[:, 1])
+    for c in range(3):
+        grids[c, ix, iy] = data[:, 2 + c]
+    return {"fixed": head[0], "fixed_value": float(head[1]), "axes": AXES[head[0]], "p1": x, "p2": y, "rows": data,
+            "gap_ratio": grids[0], "condensate_fraction": grids[1], "coherence": grids[2]}

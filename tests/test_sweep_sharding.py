@@ -96,3 +96,32 @@ def test_two_rank_sweep_equals_serial():
         p.join(timeout=60)
     assert np.array_equal(got[0], serial) and np.array_equal(got[1], serial)
     assert sorted(sw.shard(25, 2, 0) + sw.shard(25, 2, 1)) == list(range(25))
+
+
+def test_read_phase_round_trip(tmp_path):
+    """Reader side of the phase.txt contract: every committed reference file parses, write -> read is the identity at the
+    file's 6-digit precision, and a half-written file (a sweep interrupted under --resume) gives NaN for the missing points."""
+    sw = sweep_mod()
+    for name, fixed, shape in [("phase_m5_fJ.txt", "J", (3, 3)), ("phase_m5_fU.txt", "U", (3, 3)), ("phase_m5_fu.txt", "u", None),
+                               ("phase_m8_C1.txt", "J", (11, 11)), ("phase_m10_fJ.txt", "J", None)]:
+        ph = sw.read_phase(os.path.join(GOLD, name))
+        assert ph["fixed"] == fixed and ph["axes"] == sw.AXES[fixed]
+        if shape:
+            assert ph["gap_ratio"].shape == shape and not np.isnan(ph["gap_ratio"]).any()
+        # row k = i1 * n2 + i2 in writing order (full rectangular grids only)
+        n1, n2 = len(ph["p1"]), len(ph["p2"])
+        if len(ph["rows"]) == n1 * n2:
+            assert np.array_equal(ph["coherence"].reshape(-1), ph["rows"][:, 4])
+            assert np.array_equal(ph["condensate_fraction"].reshape(-1), ph["rows"][:, 3])
+        out = tmp_path / name
+        sw.write_phase(str(out), {"fixed": ph["fixed"], "fixed_value": ph["fixed_value"]}, ph["rows"])
+        assert open(out).read() == open(os.path.join(GOLD, name)).read()
+    text = open(os.path.join(GOLD, "phase_m8_C1.txt")).read().split("\n")
+    part = tmp_path / "partial.txt"
+    part.write_text("\n".join(text[:1 + 60]) + "\n")
+    ph = sw.read_phase(str(part))
+    assert len(ph["rows"]) == 60 and np.isnan(ph["gap_ratio"]).sum() == ph["gap_ratio"].size - 60
+    bad = tmp_path / "bad.txt"
+    bad.write_text("X 1\n1 2 3 4 5\n")
+    with pytest.raises(ValueError):
+        sw.read_phase(str(bad))
