@@ -138,7 +138,9 @@ struct bh_ctx {
     int cheb_quick = 24;   // quick stage 1 for D >= 50000: one cycle of this many plain steps locates E_0 (0 = always the full stage 1; env BH_CHEB_QUICK)
     int cheb_pre = 3;      // plain restart cycles run first to locate the wanted end of the spectrum (env BH_CHEB_PRE)
     double cheb_margin = 0.05;  // cut >= theta_{nev-1} + margin * (theta_{nev-1} - theta_0)   (env BH_CHEB_MARGIN)
-    double cheb_frac = 0.08;    // cut >= theta_0 + frac * (hi - theta_0)                       (env BH_CHEB_FRAC)
+    double cheb_frac = 0.05;    // cut >= theta_0 + frac * (hi - theta_0)                       (env BH_CHEB_FRAC)
+    int cheb_stall_iter = 0;    // > 0 while a quick-mode stage 2 runs: give up once this many restarts have left the nev-th Ritz
+                                // value of the filtered operator inside the damped band (> -1): the cut sits below E_{nev-1}
     double* d_cheb[3] = {nullptr, nullptr, nullptr};
     int rr_gram = 1;                 // Rayleigh-Ritz of H: W = H V, then one Gram pass V^T W (env BH_RR_GRAM; 0 = ncv transposed products)
     double* d_hv_block = nullptr;    // W, hv_block_cols columns of ld doubles (lazy)

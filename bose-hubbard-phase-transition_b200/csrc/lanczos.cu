@@ -1045,6 +1045,10 @@ static int lanczos_core(bh_ctx* ctx, const LanczosOp& op, bool start_given, int 
             nconv += (resid < thresh);
         }
         if (nconv >= nev || iter >= maxit) break;
+        // quick-mode filter with a misplaced cut (tools/model_cut.py): a healthy run has the nev-th Ritz value below -1 after the
+        // FIRST cycle, a cut below E_{nev-1} keeps it inside the damped band for ever -- stop after a few cycles instead of 80
+        // (>= 80 filtered steps as well: with a short basis, e.g. nev = 2 / ncv = 12, three cycles are too few to judge)
+        if (ctx->cheb_stall_iter > 0 && iter >= ctx->cheb_stall_iter && nmatvec >= 80 && evals[nev - 1] > -1.0) break;
         ++iter;
         // HermEigsBase.h:172-196
         int knew = nev;
@@ -1171,7 +1175,9 @@ static int accel_solve(bh_ctx* ctx, const LanczosOp& plain, int& hv_count, doubl
         return (int)BH_OK;
     };
     BhSolve s2;
+    ctx->cheb_stall_iter = quick ? 2 : 0;
     rc = lanczos_core(ctx, cheb, true, nev, ncv, tol, quick ? std::min(maxit, 80) : maxit, &s2);
+    ctx->cheb_stall_iter = 0;
     const int restarts = s1.info.nrestart + s2.info.nrestart;
     if (rc == BH_ERR_NOCONV && quick) {  // a misplaced cut stalls the filtered iteration: full stage 1
         *retry = true;

@@ -618,6 +618,9 @@ int bh_points_small(bh_ctx* ctx, int64_t npoints, const double* cJ, const double
                         nconv += (std::fabs(Y[(nv - 1) + (size_t)l * nv]) * beta_last < thresh);
                     }
                     sp.init = 0;
+                    // misplaced cut of the quick form (lanczos_core has the same rule): the nev-th Ritz value of the filtered
+                    // operator is still inside the damped band after three cycles -> the single-point path retries in full
+                    if (sp.stage == 2 && sp.quick && nconv < ne && sp.iter >= 2 && sp.nsteps >= 80 + ctx->cheb_quick && evals[ne - 1] > -1.0) { sp.stage = 6; return; }
                     if (nconv >= ne || sp.iter >= sp.maxit) {
                         sp.nrestart += sp.iter + 1;
                         sp.evals = evals;
