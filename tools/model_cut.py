@@ -7,11 +7,13 @@
 
     python tools/model_cut.py M U[,U..]
 """
+import os
 import sys
 
 import numpy as np
 import scipy.sparse as sp
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from model_block_lanczos import Counter, build_H, cheb_op, tr_block_lanczos
 
 
