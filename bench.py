@@ -147,7 +147,7 @@ def reference_sample(maxit, threads):
     }
 
 
-def reference_converged(threads, budget_s=1000):
+def reference_converged(threads, budget_s=1300):
     """`npts` grid points of C3 (U = 1..npts, mu = 0; one per core, at most 12) through the reference's per-point loop body
     (src/analysis.cpp:302-343 via oracle/_ref/ref_harness points) to CONVERGENCE: a measured points/s, no extrapolation.
     The measurement is a property of the host: it is cached in /tmp for the other N of a scaling run on the same box."""
